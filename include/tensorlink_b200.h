@@ -1,0 +1,114 @@
+/* tensorlink_b200 — C ABI of the B200-native shard executor.
+ *
+ * The reference (tensorlink-lab/tensorlink) has no FFI: its shard operator is Python
+ * (`LayerGroupModule.forward(**kwargs)`, tensorlink/ml/injector.py:154-281) and the arithmetic is
+ * whatever Hugging Face `transformers` does inside `decoder_layer(...)`.  This header is the plain-C
+ * boundary that sits UNDER that operator: every entry point replaces one group of ATen library calls
+ * the reference's worker makes per layer (`module(**kwargs)`, tensorlink/ml/worker.py:333) or its
+ * autograd (`assoc_output.backward(loss)`, tensorlink/ml/worker.py:271).  INTEGRATION.md shows the
+ * ctypes binding a maintainer would add on the reference side.
+ *
+ * Conventions
+ *  - all pointers are DEVICE pointers on the current device unless the name ends in `_host`;
+ *    bf16 tensors are `void*`; row-major, innermost dimension contiguous, 16-byte aligned.
+ *  - `stream` is a `cudaStream_t` passed as `void*`; every call is asynchronous on that stream.
+ *  - no entry point allocates or frees device memory; workspaces are passed in.
+ *  - return value: 0 on success, a negative `tl_status` otherwise; `tl_last_error()` gives the
+ *    (thread-local) message.  There is no CPU fallback: on a machine without an sm_100 device
+ *    compute calls return TL_ERR_NO_DEVICE.
+ *  - rounding points replicate the reference's bf16 pipeline (each HF op output is rounded to bf16
+ *    before the next op consumes it); accumulation is fp32.
+ */
+#ifndef TENSORLINK_B200_H
+#define TENSORLINK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TL_ABI_VERSION 1
+
+typedef enum {
+    TL_OK = 0,
+    TL_ERR_INVALID = -1,   /* bad shape / alignment / flag combination */
+    TL_ERR_CUDA = -2,      /* a CUDA runtime / driver call failed       */
+    TL_ERR_NO_DEVICE = -3, /* no sm_100 device visible                  */
+    TL_ERR_WORKSPACE = -4  /* workspace too small                       */
+} tl_status;
+
+/* epilogue / operand flags for tl_gemm_bf16 and tl_gemv_bf16 */
+#define TL_EPI_BIAS 1      /* + bias[N] (bf16), added in fp32 before the output rounding (oneDNN post-op)  */
+#define TL_EPI_RESIDUAL 2  /* out = bf16(bf16(acc) + residual[M,N])  — HF `residual + hidden_states`        */
+#define TL_EPI_SWIGLU 4    /* rows of B interleave gate/up (2j, 2j+1); out[M,N/2] = silu(gate)*up, HF rounding */
+#define TL_EPI_OUT_F32 8   /* C is fp32 instead of bf16                                                     */
+#define TL_EPI_ACCUM 16    /* C += result (bf16 read-modify-write; gradient accumulation)                   */
+#define TL_A_MN_MAJOR 32   /* A is given as [K, M] row-major (contraction dim outermost)                     */
+#define TL_B_MN_MAJOR 64   /* B is given as [K, N] row-major                                                 */
+
+int tl_abi_version(void);
+const char* tl_last_error(void);
+/* sm_count / compute capability of the current device; TL_ERR_NO_DEVICE if none */
+int tl_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- K1  Qwen2RMSNorm.forward (site-packages/transformers/models/qwen2/modeling_qwen2.py:258-263)
+ * y[r,:] = w * bf16(x[r,:] * rsqrt(mean(x[r,:]^2) + eps)); rstd_out (fp32[rows]) optional, for backward */
+int tl_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd_out, int rows, int H, float eps, void* stream);
+
+/* ---- K7  embed_tokens gather (modeling_qwen2.py:367): out[n,:] = table[ids[n],:] */
+int tl_embed_fwd(const int64_t* ids, const void* table, void* out, int n_tokens, int H, int vocab, void* stream);
+
+/* ---- K2/K5/K6/K7  nn.Linear as one tcgen05 GEMM: C[M,N] = A[M,K] * B[N,K]^T (+ epilogue flags above).
+ * lda/ldb/ldc in elements.  Replaces q/k/v_proj (modeling_qwen2.py:217-219, fused into one B), o_proj (:244),
+ * gate/up/down_proj (:46-48), lm_head (:474-476) and, with the MN-major flags, their dgrad/wgrad. */
+int tl_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
+                 const void* bias, const void* residual, int flags, void* stream);
+
+/* ---- decode-shaped Linear (M <= 8 tokens), HBM-bound weight streaming:
+ * y[M,N] = f(norm(x)[M,K] * W[N,K]^T).  norm_w != NULL fuses the preceding RMSNorm (K1) as a prologue. */
+int tl_gemv_bf16(const void* x, const void* W, void* y, int M, int N, int K, const void* bias,
+                 const void* residual, const void* norm_w, float eps, int flags, void* stream);
+
+/* ---- K3  rotary tables (modeling_qwen2.py:102-113): cos/sin[pos, d/2] = bf16(cos/sin(pos * inv_freq)) */
+int tl_rope_table(const float* inv_freq, void* cos_tab, void* sin_tab, int max_pos, int half_dim, void* stream);
+
+/* ---- K3 + KV-cache append (+ Qwen3 q/k RMSNorm, modeling_qwen3.py:248-264):
+ * qkv[n, (n_h+2n_kv)*d] (post-bias) -> q_out[n, n_h*d] rotated; K/V written to
+ * cache[b, kv_head, pos, d] with b = n / S, pos = pos0[b or 0] + n % S (pos0 read from device memory so a
+ * captured CUDA graph can be replayed while the position advances). q_norm_w/k_norm_w may be NULL. */
+int tl_rope_kv_fwd(const void* qkv, void* q_out, void* k_cache, void* v_cache, const int32_t* pos0_dev,
+                   const void* cos_tab, const void* sin_tab, const void* q_norm_w, const void* k_norm_w,
+                   float eps, int n_tokens, int S, int n_h, int n_kv, int d, int T_max, void* stream);
+
+/* ---- K4  causal GQA attention, prefill / training forward (modeling_qwen2.py:161-184 SDPA contract).
+ * q[B,S,n_h,d]; caches [B,n_kv,T_max,d] hold keys 0..past_len+S-1; out[B,S,n_h*d];
+ * lse (fp32 [B,n_h,S], natural log) optional, kept for backward. */
+int tl_attn_prefill_fwd(const void* q, const void* k_cache, const void* v_cache, void* out, float* lse, int B,
+                        int S, int past_len, int n_h, int n_kv, int d, int T_max, float scale, void* stream);
+
+/* ---- K4  decode attention, one query token per batch row, split over the KV length.
+ * kv_len_dev: device int32, number of valid keys (same for all rows).  workspace >= tl_attn_decode_ws(...) */
+size_t tl_attn_decode_ws(int B, int n_h, int d, int T_max);
+int tl_attn_decode_fwd(const void* q, const void* k_cache, const void* v_cache, void* out,
+                       const int32_t* kv_len_dev, void* workspace, size_t ws_bytes, int B, int n_h, int n_kv,
+                       int d, int T_max, float scale, void* stream);
+
+/* ---- K7  final norm + lm_head + greedy argmax for M <= 8 rows: ids[m] = argmax_v bf16(norm(x)[m,:]·W[v,:])
+ * (lowest index wins ties, as torch.argmax).  logits_out (bf16 [M,V]) optional.
+ * workspace >= tl_lmhead_ws(M, V) bytes. */
+size_t tl_lmhead_ws(int M, int V);
+int tl_lmhead_argmax(const void* x, const void* W, const void* norm_w, float eps, int64_t* ids_out,
+                     void* logits_out, void* workspace, size_t ws_bytes, int M, int V, int H, void* stream);
+
+/* argmax over bf16 logits[M,V] (any M); workspace >= M*64*8 bytes */
+int tl_argmax_bf16(const void* logits, int64_t* ids_out, void* workspace, size_t ws_bytes, int M, int V, void* stream);
+
+/* ---- small device-side helpers used by the captured decode graph */
+int tl_advance_pos(int32_t* pos_dev, int32_t* kv_len_dev, int delta, void* stream); /* pos += delta; kv_len = pos */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TENSORLINK_B200_H */

@@ -1,0 +1,398 @@
+// nn.Linear and its gradients as one persistent, warp-specialised tcgen05 GEMM.
+//
+//   C[M,N] (+)= A[M,K] · B[N,K]^T        bf16 operands, fp32 accumulation in TMEM
+//
+// CTA = 6 warps: warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer, warps 2..5 = epilogue
+// (TMEM lane quarter = warp_id % 4).  128 x BN output tile, BLOCK_K = 64 (one 128-byte swizzle atom of bf16),
+// STAGES-deep smem ring fed by cp.async.bulk.tensor, two TMEM accumulators so the epilogue of tile i overlaps
+// the MMAs of tile i+1.  Operands may be K-major (row-major [rows, K]) or MN-major (row-major [K, rows]) so the
+// same kernel serves forward (x·W^T), dgrad (dy·W) and wgrad (dy^T·x) without transposes.
+// Tensor-core roofline: 2*M*N*K flops per launch.
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+
+namespace tl {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int GEMM_THREADS = 192;
+
+// ---------------------------------------------------------------------------------------- tensor maps (host)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        else
+            cudaGetLastError();
+    });
+    return fn;
+}
+
+struct MapKey {
+    const void* ptr;
+    uint64_t inner, outer, ld;
+    uint32_t box_inner, box_outer;
+    bool operator==(const MapKey& o) const {
+        return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner &&
+               box_outer == o.box_outer;
+    }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        size_t h = (size_t)k.ptr;
+        h = h * 1000003u ^ k.inner;
+        h = h * 1000003u ^ k.outer;
+        h = h * 1000003u ^ k.ld;
+        h = h * 1000003u ^ ((uint64_t)k.box_inner << 32 | k.box_outer);
+        return h;
+    }
+};
+
+// 2-D bf16 row-major tensor [outer, inner] with leading dimension ld (elements); 128B-swizzled boxes
+static int make_tensor_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
+                           uint32_t box_inner, uint32_t box_outer) {
+    static std::mutex mu;
+    static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+    MapKey key{ptr, inner, outer, ld, box_inner, box_outer};
+    {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) {
+            *out = it->second;
+            return TL_OK;
+        }
+    }
+    EncodeTiledFn enc = get_encode_fn();
+    TL_REQUIRE(enc != nullptr, TL_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    TL_REQUIRE(((uintptr_t)ptr & 15) == 0 && (ld * 2) % 16 == 0, TL_ERR_INVALID,
+               "GEMM operand must be 16-byte aligned with a 16-byte-multiple row pitch (ptr=%p ld=%llu)", ptr,
+               (unsigned long long)ld);
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TL_REQUIRE(r == CUDA_SUCCESS, TL_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) inner=%llu outer=%llu ld=%llu",
+               (int)r, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld);
+    std::lock_guard<std::mutex> g(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache[key] = *out;
+    return TL_OK;
+}
+
+// ---------------------------------------------------------------------------------------- kernel
+template <int BN>
+struct GemmCfg {
+    static constexpr int A_BYTES = BM * BK * 2;         // 16 KB
+    static constexpr int B_BYTES = BN * BK * 2;         // 16 / 32 KB
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr int TMEM_COLS = 2 * BN;            // two accumulators
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, void* __restrict__ Cv,
+                 int M, int N, int K, int ldc, const bf16* __restrict__ bias, const bf16* __restrict__ residual,
+                 int ldr, int flags) {
+    using Cfg = GemmCfg<BN>;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full_bar = bars;                         // [STAGES]
+    uint64_t* empty_bar = bars + Cfg::STAGES;          // [STAGES]
+    uint64_t* tmem_full = bars + 2 * Cfg::STAGES;      // [2]
+    uint64_t* tmem_empty = bars + 2 * Cfg::STAGES + 2; // [2]
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+    const int total_tiles = tiles_m * tiles_n;
+    const int num_k = (K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < Cfg::STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 4);   // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_base_slot);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    unsigned char* sa = smem + stage * Cfg::STAGE_BYTES;
+                    unsigned char* sb = sa + Cfg::A_BYTES;
+                    mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    if (!A_MN) {
+                        tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BM / 64; ++j)
+                            tma_load_2d(sa + j * 8192, &tmA, &full_bar[stage], m0 + 64 * j, kb * BK);
+                    }
+                    if (!B_MN) {
+                        tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j)
+                            tma_load_2d(sb + j * 8192, &tmB, &full_bar[stage], n0 + 64 * j, kb * BK);
+                    }
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer (one thread)
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint32_t sb = sa + Cfg::A_BYTES;
+                    // K-major: 8-row groups 1024 B apart (SBO), LBO unused(=16 B), k-step = 32 B inside the atom
+                    // MN-major: 64-element MN chunks 8192 B apart (LBO), 8-k groups 1024 B apart (SBO), k-step = 2 KB
+                    const uint64_t da = A_MN ? make_smem_desc_sw128(sa, 8192, 1024) : make_smem_desc_sw128(sa, 16, 1024);
+                    const uint64_t db = B_MN ? make_smem_desc_sw128(sb, 8192, 1024) : make_smem_desc_sw128(sb, 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t ak = da + (uint64_t)((A_MN ? 2048 : 32) * k >> 4);
+                        const uint64_t bk = db + (uint64_t)((B_MN ? 2048 : 32) * k >> 4);
+                        umma_bf16(d_tmem, ak, bk, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
+                    if (kb == num_k - 1) umma_commit(&tmem_full[acc]);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================================================================== epilogue warps (TMEM -> regs -> HBM)
+        const int quarter = warp & 3;                  // TMEM lanes [32*quarter, 32*quarter+32)
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const bool swiglu = flags & TL_EPI_SWIGLU;
+        const bool out_f32 = flags & TL_EPI_OUT_F32;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tcgen05_fence_after();
+            const int row = m0 + quarter * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(taddr + (uint32_t)(c * 32), r);
+                tmem_ld_wait();
+                const int col0 = n0 + c * 32;
+                if (row < M && col0 < N) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    const int ncols = min(32, N - col0);
+                    if (flags & TL_EPI_BIAS) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < ncols) v[j] += bf2f(bias[col0 + j]);
+                    }
+                    if (swiglu) {
+                        // interleaved (gate, up) column pairs -> 16 outputs
+                        bf16* dst = reinterpret_cast<bf16*>(Cv) + (size_t)row * ldc + (col0 >> 1);
+                        uint32_t o[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float g0 = rbf(v[4 * j]), u0 = rbf(v[4 * j + 1]);
+                            const float g1 = rbf(v[4 * j + 2]), u1 = rbf(v[4 * j + 3]);
+                            o[j] = pack_bf16(rbf(silu_f(g0)) * u0, rbf(silu_f(g1)) * u1);
+                        }
+                        if (ncols == 32) {
+                            reinterpret_cast<uint4*>(dst)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                            reinterpret_cast<uint4*>(dst)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                        } else {
+                            for (int j = 0; j < ncols / 2; ++j)
+                                dst[j] = reinterpret_cast<bf16*>(o)[j];
+                        }
+                    } else if (out_f32) {
+                        float* dst = reinterpret_cast<float*>(Cv) + (size_t)row * ldc + col0;
+                        if (flags & TL_EPI_ACCUM) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j < ncols) v[j] += dst[j];
+                        }
+                        if (ncols == 32) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        } else {
+                            for (int j = 0; j < ncols; ++j) dst[j] = v[j];
+                        }
+                    } else {
+                        bf16* dst = reinterpret_cast<bf16*>(Cv) + (size_t)row * ldc + col0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = rbf(v[j]);     // the Linear's own bf16 output
+                        if (flags & TL_EPI_RESIDUAL) {
+                            const bf16* rs = residual + (size_t)row * ldr + col0;
+                            if (ncols == 32) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const uint4 u = reinterpret_cast<const uint4*>(rs)[q];
+                                    const uint32_t* u32 = reinterpret_cast<const uint32_t*>(&u);
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        v[8 * q + 2 * j] += bf16_lo(u32[j]);
+                                        v[8 * q + 2 * j + 1] += bf16_hi(u32[j]);
+                                    }
+                                }
+                            } else {
+                                for (int j = 0; j < ncols; ++j) v[j] += bf2f(rs[j]);
+                            }
+                        }
+                        if (flags & TL_EPI_ACCUM) {
+                            if (ncols == 32) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const uint4 u = reinterpret_cast<const uint4*>(dst)[q];
+                                    const uint32_t* u32 = reinterpret_cast<const uint32_t*>(&u);
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        v[8 * q + 2 * j] += bf16_lo(u32[j]);
+                                        v[8 * q + 2 * j + 1] += bf16_hi(u32[j]);
+                                    }
+                                }
+                            } else {
+                                for (int j = 0; j < ncols; ++j) v[j] += bf2f(dst[j]);
+                            }
+                        }
+                        if (ncols == 32) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                reinterpret_cast<uint4*>(dst)[q] =
+                                    make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
+                                               pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+                        } else {
+                            for (int j = 0; j < ncols; ++j) dst[j] = f2bf(v[j]);
+                        }
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
+                       const void* bias, const void* residual, int flags, cudaStream_t st) {
+    using Cfg = GemmCfg<BN>;
+    CUtensorMap tmA, tmB;
+    int rc;
+    // K-major operand [rows, K]: inner = K, box = (64, rows-per-tile).  MN-major operand [K, rows]: inner = rows,
+    // box = (64 rows, 64 k).
+    rc = A_MN ? make_tensor_map(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, BK)
+              : make_tensor_map(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM);
+    if (rc != TL_OK) return rc;
+    rc = B_MN ? make_tensor_map(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BK)
+              : make_tensor_map(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, BN);
+    if (rc != TL_OK) return rc;
+    auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
+            return check_launch("tl_gemm_bf16 (smem attr)");
+        attr_done = true;
+    }
+    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    const int ldr = ldc;
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, C, M, N, K, ldc, (const bf16*)bias,
+                                                      (const bf16*)residual, ldr, flags);
+    return check_launch("tl_gemm_bf16");
+}
+
+template <int BN>
+static int dispatch_major(bool a_mn, bool b_mn, const void* A, const void* B, void* C, int M, int N, int K, int lda,
+                          int ldb, int ldc, const void* bias, const void* residual, int flags, cudaStream_t st) {
+    if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(A, B, C, M, N, K, lda, ldb, ldc, bias, residual, flags, st);
+    if (!a_mn && b_mn) return launch_gemm<BN, false, true>(A, B, C, M, N, K, lda, ldb, ldc, bias, residual, flags, st);
+    if (a_mn && !b_mn) return launch_gemm<BN, true, false>(A, B, C, M, N, K, lda, ldb, ldc, bias, residual, flags, st);
+    return launch_gemm<BN, true, true>(A, B, C, M, N, K, lda, ldb, ldc, bias, residual, flags, st);
+}
+
+}  // namespace tl
+
+extern "C" int tl_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
+                            const void* bias, const void* residual, int flags, void* stream) {
+    using namespace tl;
+    TL_REQUIRE(M > 0 && N > 0 && K > 0, TL_ERR_INVALID, "tl_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
+    TL_REQUIRE(K % 8 == 0 && N % 8 == 0, TL_ERR_INVALID, "tl_gemm_bf16: N and K must be multiples of 8 (N=%d K=%d)",
+               N, K);
+    TL_REQUIRE(!(flags & TL_EPI_BIAS) || bias, TL_ERR_INVALID, "tl_gemm_bf16: BIAS flag without bias pointer");
+    TL_REQUIRE(!(flags & TL_EPI_RESIDUAL) || residual, TL_ERR_INVALID, "tl_gemm_bf16: RESIDUAL flag without pointer");
+    const bool swiglu = flags & TL_EPI_SWIGLU;
+    TL_REQUIRE(!swiglu || !(flags & (TL_EPI_RESIDUAL | TL_EPI_OUT_F32 | TL_EPI_ACCUM)), TL_ERR_INVALID,
+               "tl_gemm_bf16: SWIGLU excludes RESIDUAL/OUT_F32/ACCUM");
+    TL_REQUIRE(!swiglu || N % 16 == 0, TL_ERR_INVALID, "tl_gemm_bf16: SWIGLU needs N %% 16 == 0");
+    const int c_cols = swiglu ? N / 2 : N;
+    TL_REQUIRE(ldc >= c_cols && ldc % 8 == 0, TL_ERR_INVALID, "tl_gemm_bf16: ldc=%d too small / unaligned", ldc);
+    const bool a_mn = flags & TL_A_MN_MAJOR, b_mn = flags & TL_B_MN_MAJOR;
+    TL_REQUIRE(lda >= (a_mn ? M : K) && ldb >= (b_mn ? N : K), TL_ERR_INVALID, "tl_gemm_bf16: lda/ldb too small");
+    TL_REQUIRE((!a_mn || M % 8 == 0), TL_ERR_INVALID, "tl_gemm_bf16: MN-major A needs M %% 8 == 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    // 128x256 tiles when they still fill the machine, else 128x128
+    const long long tiles256 = (long long)((M + BM - 1) / BM) * ((N + 255) / 256);
+    const bool use256 = (N >= 256) && tiles256 >= (long long)sm_count();
+    if (use256) return dispatch_major<256>(a_mn, b_mn, A, B, C, M, N, K, lda, ldb, ldc, bias, residual, flags, st);
+    return dispatch_major<128>(a_mn, b_mn, A, B, C, M, N, K, lda, ldb, ldc, bias, residual, flags, st);
+}

@@ -1,0 +1,245 @@
+"""ctypes binding of ``libtensorlink_b200.so`` (the C ABI in ``include/tensorlink_b200.h``).
+
+There is no CPU fallback and no eager-PyTorch twin: if the library is missing, or no sm_100 device is
+visible, every compute entry point raises.  PyTorch is used only to own device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libtensorlink_b200.so")
+
+EPI_BIAS, EPI_RESIDUAL, EPI_SWIGLU, EPI_OUT_F32, EPI_ACCUM, A_MN_MAJOR, B_MN_MAJOR = 1, 2, 4, 8, 16, 32, 64
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_SIGS = {
+    "tl_abi_version": (c_int, []),
+    "tl_last_error": (c_char_p, []),
+    "tl_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "tl_rmsnorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
+    "tl_embed_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "tl_gemm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                             c_void_p, c_void_p, c_int, c_void_p]),
+    "tl_gemv_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                             c_float, c_int, c_void_p]),
+    "tl_rope_table": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "tl_rope_kv_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_float, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "tl_attn_prefill_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                    c_int, c_int, c_int, c_float, c_void_p]),
+    "tl_attn_decode_ws": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "tl_attn_decode_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int,
+                                   c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "tl_lmhead_ws": (c_size_t, [c_int, c_int]),
+    "tl_lmhead_argmax": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_size_t,
+                                 c_int, c_int, c_int, c_void_p]),
+    "tl_argmax_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
+    "tl_advance_pos": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+}
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library and bind every declared symbol (no device needed for this)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(tensorlink_b200 has no CPU or eager fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)       # AttributeError here = header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return sorted(_SIGS)
+
+
+def last_error() -> str:
+    return (load().tl_last_error() or b"").decode()
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise NativeError(f"{what} failed ({rc}): {last_error()}")
+
+
+_device_ok = False
+
+
+def require_device():
+    """Raise unless a B200-class (sm_100) device is current."""
+    global _device_ok
+    if _device_ok:
+        return
+    if not torch.cuda.is_available():
+        raise NativeError("no CUDA device: the tensorlink_b200 shard executor runs on sm_100a only")
+    sm, ma, mi = c_int(), c_int(), c_int()
+    _check(load().tl_device_info(sm, ma, mi), "tl_device_info")
+    _device_ok = True
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    assert t.is_cuda, "device tensor expected"
+    return t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _bf16(*ts):
+    for t in ts:
+        if t is not None:
+            assert t.dtype == torch.bfloat16 and t.is_contiguous(), (t.dtype, t.is_contiguous())
+
+
+# ------------------------------------------------------------------------------------------ thin typed wrappers
+def rmsnorm_fwd(x: torch.Tensor, w: torch.Tensor, eps: float, out: Optional[torch.Tensor] = None,
+                rstd: Optional[torch.Tensor] = None) -> torch.Tensor:
+    require_device()
+    _bf16(x, w, out)
+    H = x.shape[-1]
+    rows = x.numel() // H
+    out = torch.empty_like(x) if out is None else out
+    _check(load().tl_rmsnorm_fwd(_p(x), _p(w), _p(out), _p(rstd), rows, H, eps, _stream()), "tl_rmsnorm_fwd")
+    return out
+
+
+def embed_fwd(ids: torch.Tensor, table: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    require_device()
+    assert ids.dtype == torch.int64 and ids.is_contiguous()
+    _bf16(table, out)
+    V, H = table.shape
+    n = ids.numel()
+    out = torch.empty(*ids.shape, H, dtype=torch.bfloat16, device=table.device) if out is None else out
+    _check(load().tl_embed_fwd(_p(ids), _p(table), _p(out), n, H, V, _stream()), "tl_embed_fwd")
+    return out
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *, bias=None, residual=None,
+         flags: int = 0, M: Optional[int] = None, N: Optional[int] = None, K: Optional[int] = None) -> torch.Tensor:
+    """C[M,N] = A·B^T with the epilogue ``flags``.  A is [M,K] (or [K,M] with A_MN_MAJOR), B is [N,K] (or [K,N])."""
+    require_device()
+    _bf16(a, b, bias, residual)
+    a_mn, b_mn = bool(flags & A_MN_MAJOR), bool(flags & B_MN_MAJOR)
+    if M is None:
+        M = a.shape[1] if a_mn else a.shape[0]
+    if K is None:
+        K = a.shape[0] if a_mn else a.shape[1]
+    if N is None:
+        N = b.shape[1] if b_mn else b.shape[0]
+    c_cols = N // 2 if flags & EPI_SWIGLU else N
+    if out is None:
+        out = torch.empty(M, c_cols, dtype=torch.float32 if flags & EPI_OUT_F32 else torch.bfloat16, device=a.device)
+    if bias is not None:
+        flags |= EPI_BIAS
+    if residual is not None:
+        flags |= EPI_RESIDUAL
+    _check(load().tl_gemm_bf16(_p(a), _p(b), _p(out), M, N, K, a.stride(0), b.stride(0), out.stride(0), _p(bias),
+                               _p(residual), flags, _stream()), "tl_gemm_bf16")
+    return out
+
+
+def gemv(x: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, *, bias=None, residual=None,
+         norm_w=None, eps: float = 1e-6, flags: int = 0) -> torch.Tensor:
+    require_device()
+    _bf16(x, w, bias, residual, norm_w, out)
+    M, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty(M, N // 2 if flags & EPI_SWIGLU else N, dtype=torch.bfloat16, device=x.device)
+    if bias is not None:
+        flags |= EPI_BIAS
+    if residual is not None:
+        flags |= EPI_RESIDUAL
+    _check(load().tl_gemv_bf16(_p(x), _p(w), _p(out), M, N, K, _p(bias), _p(residual), _p(norm_w), eps, flags,
+                               _stream()), "tl_gemv_bf16")
+    return out
+
+
+def rope_table(inv_freq: torch.Tensor, max_pos: int):
+    require_device()
+    assert inv_freq.dtype == torch.float32 and inv_freq.is_cuda
+    half = inv_freq.numel()
+    cos = torch.empty(max_pos, half, dtype=torch.bfloat16, device=inv_freq.device)
+    sin = torch.empty_like(cos)
+    _check(load().tl_rope_table(_p(inv_freq), _p(cos), _p(sin), max_pos, half, _stream()), "tl_rope_table")
+    return cos, sin
+
+
+def rope_kv_fwd(qkv, q_out, k_cache, v_cache, pos0_dev, cos_tab, sin_tab, q_norm_w, k_norm_w, eps, S, n_h, n_kv, d):
+    require_device()
+    _bf16(qkv, q_out, k_cache, v_cache, cos_tab, sin_tab, q_norm_w, k_norm_w)
+    n_tokens = qkv.shape[0]
+    T_max = k_cache.shape[2]
+    _check(load().tl_rope_kv_fwd(_p(qkv), _p(q_out), _p(k_cache), _p(v_cache), _p(pos0_dev), _p(cos_tab), _p(sin_tab),
+                                 _p(q_norm_w), _p(k_norm_w), eps, n_tokens, S, n_h, n_kv, d, T_max, _stream()),
+           "tl_rope_kv_fwd")
+
+
+def attn_prefill_fwd(q, k_cache, v_cache, out, lse, B, S, past_len, n_h, n_kv, d, scale):
+    require_device()
+    _bf16(q, k_cache, v_cache, out)
+    T_max = k_cache.shape[2]
+    _check(load().tl_attn_prefill_fwd(_p(q), _p(k_cache), _p(v_cache), _p(out), _p(lse), B, S, past_len, n_h, n_kv, d,
+                                      T_max, scale, _stream()), "tl_attn_prefill_fwd")
+
+
+def attn_decode_ws(B, n_h, d, T_max) -> int:
+    return int(load().tl_attn_decode_ws(B, n_h, d, T_max))
+
+
+def attn_decode_fwd(q, k_cache, v_cache, out, kv_len_dev, ws, B, n_h, n_kv, d, scale):
+    require_device()
+    _bf16(q, k_cache, v_cache, out)
+    T_max = k_cache.shape[2]
+    _check(load().tl_attn_decode_fwd(_p(q), _p(k_cache), _p(v_cache), _p(out), _p(kv_len_dev), _p(ws),
+                                     ws.numel() * ws.element_size(), B, n_h, n_kv, d, T_max, scale, _stream()),
+           "tl_attn_decode_fwd")
+
+
+def lmhead_ws(M, V) -> int:
+    return int(load().tl_lmhead_ws(M, V))
+
+
+def lmhead_argmax(x, w, norm_w, eps, ids_out, logits_out, ws):
+    require_device()
+    _bf16(x, w, norm_w, logits_out)
+    M, H = x.shape
+    V = w.shape[0]
+    assert ids_out.dtype == torch.int64
+    _check(load().tl_lmhead_argmax(_p(x), _p(w), _p(norm_w), eps, _p(ids_out), _p(logits_out), _p(ws),
+                                   ws.numel() * ws.element_size(), M, V, H, _stream()), "tl_lmhead_argmax")
+
+
+def argmax_bf16(logits, ids_out, ws):
+    require_device()
+    _bf16(logits)
+    M, V = logits.shape
+    _check(load().tl_argmax_bf16(_p(logits), _p(ids_out), _p(ws), ws.numel() * ws.element_size(), M, V, _stream()),
+           "tl_argmax_bf16")
+
+
+def advance_pos(pos_dev, kv_len_dev, delta: int):
+    require_device()
+    _check(load().tl_advance_pos(_p(pos_dev), _p(kv_len_dev), delta, _stream()), "tl_advance_pos")

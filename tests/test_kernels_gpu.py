@@ -1,0 +1,259 @@
+"""Kernel-level parity: every C-ABI entry point vs the CPU oracle's restatement of the same HF op.
+
+Tolerances (stated once, used below):
+  * ops with a single bf16 rounding point per output (norm, rope, Linear and its epilogues, embed):
+    rel-L2 <= 1e-3 against the oracle's bf16 result (north_star tolerance; measured ~1e-4: only values
+    whose fp32 accumulation order straddles a bf16 rounding boundary differ, by one ulp);
+  * attention: rel-L2 <= 2e-3 against 'sdpa_math' (the SDPA contract leaves the P rounding point
+    implementation-defined; torch's own CPU flash kernel differs from the same math by 2.7e-3,
+    tests/test_oracle_vs_hf.py) AND no less accurate than the oracle against fp32 attention;
+  * token ids: exact.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import shard_oracle as O
+from tensorlink_b200.ml import configs as C
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+TOL_ATTN = 2e-3
+
+
+@pytest.fixture(scope="module")
+def nat():
+    from tensorlink_b200 import native
+    native.require_device()
+    return native
+
+
+def rnd(*shape, seed=0, std=1.0, dtype=torch.bfloat16):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * std).to(dtype)
+
+
+def dev(t):
+    return t.cuda() if t is not None else None
+
+
+@pytest.mark.parametrize("rows,H", [(1, 896), (7, 3584), (300, 4096), (5, 128), (33, 256), (2, 8192)])
+def test_rmsnorm(nat, rows, H):
+    x, w = rnd(rows, H, seed=1, std=2.0), (1 + 0.1 * torch.randn(H)).bfloat16()
+    ref = O.rmsnorm(x, w, 1e-6)
+    rstd = torch.empty(rows, dtype=torch.float32, device="cuda")
+    got = nat.rmsnorm_fwd(dev(x), dev(w), 1e-6, rstd=rstd).cpu()
+    assert O.rel_l2(got, ref) <= TOL
+    assert (got != ref).float().mean() < 0.01
+    ref_rstd = torch.rsqrt(x.float().pow(2).mean(-1) + 1e-6)
+    assert torch.allclose(rstd.cpu(), ref_rstd, rtol=1e-5)
+
+
+def test_embed(nat):
+    table = rnd(1000, 896, seed=2)
+    ids = torch.randint(0, 1000, (3, 17))
+    got = nat.embed_fwd(dev(ids), dev(table)).cpu()
+    assert torch.equal(got, F.embedding(ids, table))
+
+
+GEMM_SHAPES = [(128, 128, 64), (128, 256, 128), (200, 264, 136), (1, 128, 64), (77, 1152, 896), (513, 896, 4864),
+               (1024, 2048, 512), (300, 4608, 3584), (4096, 1024, 256)]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_plain_and_bias(nat, M, N, K):
+    a, w, b = rnd(M, K, seed=3), rnd(N, K, seed=4, std=0.05), rnd(N, seed=5, std=0.5)
+    got = nat.gemm(dev(a), dev(w)).cpu()
+    assert O.rel_l2(got, F.linear(a, w)) <= TOL
+    got = nat.gemm(dev(a), dev(w), bias=dev(b)).cpu()
+    assert O.rel_l2(got, F.linear(a, w, b)) <= TOL
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (200, 264, 136), (513, 896, 4864)])
+def test_gemm_f32_out_exactness(nat, M, N, K):
+    a, w = rnd(M, K, seed=3), rnd(N, K, seed=4, std=0.05)
+    got = nat.gemm(dev(a), dev(w), flags=nat.EPI_OUT_F32).cpu()
+    ref = a.double() @ w.double().t()
+    assert O.rel_l2(got, ref) <= 1e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (333, 896, 896), (64, 3584, 512)])
+def test_gemm_residual(nat, M, N, K):
+    a, w, r = rnd(M, K, seed=6), rnd(N, K, seed=7, std=0.05), rnd(M, N, seed=8)
+    got = nat.gemm(dev(a), dev(w), residual=dev(r)).cpu()
+    assert O.rel_l2(got, r + F.linear(a, w)) <= TOL
+
+
+@pytest.mark.parametrize("M,I,K", [(128, 64, 64), (150, 768, 256), (96, 4864, 896)])
+def test_gemm_swiglu(nat, M, I, K):
+    x, wg, wu = rnd(M, K, seed=9), rnd(I, K, seed=10, std=0.08), rnd(I, K, seed=11, std=0.08)
+    wgu = torch.stack([wg, wu], dim=1).reshape(2 * I, K).contiguous()      # rows 2j = gate_j, 2j+1 = up_j
+    got = nat.gemm(dev(x), dev(wgu), flags=nat.EPI_SWIGLU).cpu()
+    ref = F.silu(F.linear(x, wg)) * F.linear(x, wu)
+    assert got.shape == (M, I)
+    assert O.rel_l2(got, ref) <= TOL
+
+
+def test_gemm_accumulate(nat):
+    a, w = rnd(256, 128, seed=12), rnd(384, 128, seed=13, std=0.1)
+    c0 = rnd(256, 384, seed=14)
+    c = dev(c0.clone())
+    nat.gemm(dev(a), dev(w), out=c, flags=nat.EPI_ACCUM)
+    assert O.rel_l2(c.cpu(), c0 + F.linear(a, w)) <= TOL
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 384, 192), (200, 264, 136), (1024, 896, 4864)])
+def test_gemm_mn_major_operands(nat, M, N, K):
+    """dgrad (B given as [K,N]) and wgrad (A as [K,M], B as [K,N]) layouts without explicit transposes."""
+    a, w = rnd(M, K, seed=15), rnd(N, K, seed=16, std=0.05)
+    ref = (a.double() @ w.double().t())
+    got = nat.gemm(dev(a), dev(w.t().contiguous()), flags=nat.B_MN_MAJOR | nat.EPI_OUT_F32, N=N).cpu()
+    assert O.rel_l2(got, ref) <= 1e-5, "B MN-major"
+    if M % 8 == 0:
+        got = nat.gemm(dev(a.t().contiguous()), dev(w), flags=nat.A_MN_MAJOR | nat.EPI_OUT_F32, M=M, K=K).cpu()
+        assert O.rel_l2(got, ref) <= 1e-5, "A MN-major"
+        got = nat.gemm(dev(a.t().contiguous()), dev(w.t().contiguous()),
+                       flags=nat.A_MN_MAJOR | nat.B_MN_MAJOR | nat.EPI_OUT_F32, M=M, K=K, N=N).cpu()
+        assert O.rel_l2(got, ref) <= 1e-5, "A and B MN-major"
+
+
+GEMV_SHAPES = [(1, 1152, 896), (1, 896, 4864), (2, 4608, 3584), (3, 896, 896), (4, 3584, 18944), (8, 1024, 512),
+               (1, 130, 264), (5, 2048, 1024)]
+
+
+@pytest.mark.parametrize("M,N,K", GEMV_SHAPES)
+def test_gemv_bias_residual(nat, M, N, K):
+    x, w, b, r = rnd(M, K, seed=17), rnd(N, K, seed=18, std=0.05), rnd(N, seed=19, std=0.5), rnd(M, N, seed=20)
+    assert O.rel_l2(nat.gemv(dev(x), dev(w)).cpu(), F.linear(x, w)) <= TOL
+    assert O.rel_l2(nat.gemv(dev(x), dev(w), bias=dev(b)).cpu(), F.linear(x, w, b)) <= TOL
+    assert O.rel_l2(nat.gemv(dev(x), dev(w), residual=dev(r)).cpu(), r + F.linear(x, w)) <= TOL
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 1152, 896), (2, 4608, 3584), (4, 512, 256)])
+def test_gemv_norm_prologue(nat, M, N, K):
+    x, w, b = rnd(M, K, seed=21, std=3.0), rnd(N, K, seed=22, std=0.05), rnd(N, seed=23, std=0.5)
+    g = (1 + 0.1 * torch.randn(K)).bfloat16()
+    ref = F.linear(O.rmsnorm(x, g, 1e-6), w, b)
+    got = nat.gemv(dev(x), dev(w), bias=dev(b), norm_w=dev(g), eps=1e-6).cpu()
+    assert O.rel_l2(got, ref) <= TOL
+
+
+@pytest.mark.parametrize("M,I,K", [(1, 4864, 896), (2, 768, 256), (4, 18944, 3584)])
+def test_gemv_swiglu(nat, M, I, K):
+    x, wg, wu = rnd(M, K, seed=24), rnd(I, K, seed=25, std=0.08), rnd(I, K, seed=26, std=0.08)
+    g = (1 + 0.1 * torch.randn(K)).bfloat16()
+    wgu = torch.stack([wg, wu], dim=1).reshape(2 * I, K).contiguous()
+    h = O.rmsnorm(x, g, 1e-6)
+    ref = F.silu(F.linear(h, wg)) * F.linear(h, wu)
+    got = nat.gemv(dev(x), dev(wgu), norm_w=dev(g), eps=1e-6, flags=nat.EPI_SWIGLU).cpu()
+    assert O.rel_l2(got, ref) <= TOL
+
+
+@pytest.mark.parametrize("cfg", [C.TINY_QWEN2, C.TINY_QWEN2_D128, C.TINY_QWEN3], ids=lambda c: c.name)
+@pytest.mark.parametrize("B,S,past", [(2, 24, 0), (1, 1, 77), (3, 5, 100)])
+def test_rope_kv(nat, cfg, B, S, past):
+    d, n_h, n_kv = cfg.head_dim, cfg.n_heads, cfg.n_kv_heads
+    T_max = 256
+    qkv = rnd(B * S, cfg.qkv_dim, seed=27)
+    qn = (1 + 0.1 * torch.randn(d)).bfloat16() if cfg.qk_norm else None
+    kn = (1 + 0.1 * torch.randn(d)).bfloat16() if cfg.qk_norm else None
+    q, k, v = qkv.view(B, S, -1).split([cfg.q_dim, cfg.kv_dim, cfg.kv_dim], dim=-1)
+    q, k, v = q.reshape(B, S, n_h, d), k.reshape(B, S, n_kv, d), v.reshape(B, S, n_kv, d)
+    if cfg.qk_norm:
+        q, k = O.rmsnorm(q, qn, cfg.rms_eps), O.rmsnorm(k, kn, cfg.rms_eps)
+    pos = torch.arange(past, past + S)[None].expand(B, -1)
+    cos, sin = O.rope_tables(cfg, pos, torch.bfloat16)
+    qr, kr = O.apply_rope(q.transpose(1, 2), k.transpose(1, 2), cos, sin)
+    inv = O.rope_inv_freq(cfg).cuda()
+    ct, st = nat.rope_table(inv, T_max)
+    ref_cos = O.rope_tables(cfg, torch.arange(T_max)[None], torch.bfloat16)[0][0, :, : d // 2]
+    assert (ct.cpu() != ref_cos).float().mean() < 2e-3          # cosf vs CPU cos, after bf16 rounding
+    q_out = torch.empty(B * S, cfg.q_dim, dtype=torch.bfloat16, device="cuda")
+    kc = torch.zeros(B, n_kv, T_max, d, dtype=torch.bfloat16, device="cuda")
+    vc = torch.zeros_like(kc)
+    pos0 = torch.tensor([past], dtype=torch.int32, device="cuda")
+    nat.rope_kv_fwd(dev(qkv), q_out, kc, vc, pos0, ct, st, dev(qn), dev(kn), cfg.rms_eps, S, n_h, n_kv, d)
+    assert O.rel_l2(q_out.cpu().view(B, S, n_h, d).transpose(1, 2), qr) <= TOL
+    assert O.rel_l2(kc.cpu()[:, :, past:past + S], kr) <= TOL
+    assert torch.equal(vc.cpu()[:, :, past:past + S], v.transpose(1, 2))
+    assert kc.cpu()[:, :, :past].abs().sum() == 0 and kc.cpu()[:, :, past + S:].abs().sum() == 0
+
+
+def _attn_case(B, S, past, n_h, n_kv, d, seed, std=1.0):
+    T = past + S
+    q = rnd(B, S, n_h, d, seed=seed, std=std)
+    k = rnd(B, n_kv, T, d, seed=seed + 1, std=std)
+    v = rnd(B, n_kv, T, d, seed=seed + 2)
+    ref = O.attention_sdpa_math(q.transpose(1, 2), k, v, d ** -0.5, n_h // n_kv)
+    kk, vv = O.repeat_kv(k, n_h // n_kv).float(), O.repeat_kv(v, n_h // n_kv).float()
+    s = (q.transpose(1, 2).float() @ kk.transpose(2, 3)) * d ** -0.5 + O.causal_mask(S, T, torch.float32)
+    f32 = (F.softmax(s, -1) @ vv).transpose(1, 2).reshape(B, S, -1)
+    return q, k, v, ref, f32
+
+
+@pytest.mark.parametrize("B,S,past,n_h,n_kv,d", [(2, 100, 0, 4, 2, 64), (1, 64, 0, 14, 2, 64), (1, 50, 37, 4, 2, 128),
+                                                 (2, 257, 0, 8, 2, 128), (1, 1, 200, 4, 4, 64), (1, 130, 300, 7, 1, 128)])
+def test_attn_prefill(nat, B, S, past, n_h, n_kv, d):
+    q, k, v, ref, f32 = _attn_case(B, S, past, n_h, n_kv, d, seed=30)
+    T_max = past + S + 19
+    kc = torch.zeros(B, n_kv, T_max, d, dtype=torch.bfloat16)
+    vc = torch.zeros_like(kc)
+    kc[:, :, :past + S], vc[:, :, :past + S] = k, v
+    out = torch.empty(B, S, n_h * d, dtype=torch.bfloat16, device="cuda")
+    lse = torch.empty(B, n_h, S, dtype=torch.float32, device="cuda")
+    nat.attn_prefill_fwd(dev(q), dev(kc), dev(vc), out, lse, B, S, past, n_h, n_kv, d, d ** -0.5)
+    got = out.cpu()
+    assert O.rel_l2(got, ref) <= TOL_ATTN
+    assert O.rel_l2(got, f32) <= 1.25 * O.rel_l2(ref, f32) + 1e-4
+    kk = O.repeat_kv(k, n_h // n_kv).float()
+    s = (q.transpose(1, 2).float() @ kk.transpose(2, 3)) * d ** -0.5 + O.causal_mask(S, past + S, torch.float32)
+    assert torch.allclose(lse.cpu(), torch.logsumexp(s, -1), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("B,kv_len,n_h,n_kv,d", [(1, 1, 14, 2, 64), (2, 127, 4, 2, 128), (1, 128, 28, 4, 128),
+                                                 (3, 129, 8, 8, 64), (1, 1000, 28, 4, 128), (2, 2048, 32, 8, 128)])
+def test_attn_decode(nat, B, kv_len, n_h, n_kv, d):
+    q, k, v, ref, f32 = _attn_case(B, 1, kv_len - 1, n_h, n_kv, d, seed=40)
+    T_max = kv_len + 100
+    kc = torch.zeros(B, n_kv, T_max, d, dtype=torch.bfloat16)
+    vc = torch.zeros_like(kc)
+    kc[:, :, :kv_len], vc[:, :, :kv_len] = k, v
+    kc[:, :, kv_len:] = 50.0        # poison: keys beyond kv_len must be ignored
+    out = torch.empty(B, n_h * d, dtype=torch.bfloat16, device="cuda")
+    ws = torch.empty(nat.attn_decode_ws(B, n_h, d, T_max), dtype=torch.uint8, device="cuda")
+    kvl = torch.tensor([kv_len], dtype=torch.int32, device="cuda")
+    nat.attn_decode_fwd(dev(q.reshape(B, n_h * d)), dev(kc), dev(vc), out, kvl, ws, B, n_h, n_kv, d, d ** -0.5)
+    got = out.cpu().view(B, 1, -1)
+    assert O.rel_l2(got, ref) <= TOL_ATTN
+    assert O.rel_l2(got, f32) <= 1.25 * O.rel_l2(ref, f32) + 1e-4
+
+
+@pytest.mark.parametrize("M,V,H", [(1, 1024, 256), (2, 151936, 896), (4, 2048, 512)])
+def test_lmhead_argmax(nat, M, V, H):
+    x, w = rnd(M, H, seed=50, std=2.0), rnd(V, H, seed=51, std=0.05)
+    g = (1 + 0.1 * torch.randn(H)).bfloat16()
+    ref_logits = F.linear(O.rmsnorm(x, g, 1e-6), w)
+    ids = torch.empty(M, dtype=torch.int64, device="cuda")
+    logits = torch.empty(M, V, dtype=torch.bfloat16, device="cuda")
+    ws = torch.empty(nat.lmhead_ws(M, V), dtype=torch.uint8, device="cuda")
+    nat.lmhead_argmax(dev(x), dev(w), dev(g), 1e-6, ids, logits, ws)
+    assert O.rel_l2(logits.cpu(), ref_logits) <= TOL
+    # ids must be the argmax of the logits the kernel itself produced (first index on ties) ...
+    assert torch.equal(ids.cpu(), logits.cpu().float().argmax(-1))
+    # ... and equal the oracle's wherever the oracle's top-2 margin exceeds one bf16 ulp of the top value
+    top2 = ref_logits.float().topk(2, -1).values
+    safe = (top2[:, 0] - top2[:, 1]) > top2[:, 0].abs() * 2 ** -7
+    assert torch.equal(ids.cpu()[safe], ref_logits.float().argmax(-1)[safe])
+
+
+def test_argmax_ties_pick_lowest_index(nat):
+    logits = torch.full((3, 5000), -1.0).bfloat16()
+    logits[0, [4999, 17, 3000]] = 2.0
+    logits[1, [4098, 4097]] = 0.5
+    logits[2, :] = 1.0
+    ids = torch.empty(3, dtype=torch.int64, device="cuda")
+    ws = torch.empty(3 * 64 * 8, dtype=torch.uint8, device="cuda")
+    nat.argmax_bf16(dev(logits), ids, ws)
+    assert ids.cpu().tolist() == [17, 4097, 0]
