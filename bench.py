@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""Headline benchmark: greedy generate through ``DistributedModel`` on N B200s (pipeline-sharded), tokens/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload qwen2.5-7b|qwen2.5-0.5b|...] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W
+
+A "step" = one full ``generate`` call: prefill of a PROMPT-token prompt + NEW greedy tokens for every row of the
+batch (global batch = rows_per_gpu x N micro-batches rotating through the N pipeline stages: weak scaling).
+``value`` = generated tokens / device time with the prompt already in HBM; ``e2e`` = the same through the public
+API from pinned host memory to host memory.  ``--impl reference`` times the reference's CPU shard math (the oracle
+port, all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "qwen2.5-7b": ("Qwen/Qwen2.5-7B", 32, 128),
+    "qwen2.5-0.5b": ("Qwen/Qwen2.5-0.5B", 32, 256),
+    "qwen3-8b": ("Qwen/Qwen3-8B", 32, 128),
+    "tiny": ("tiny-qwen2-d128", 16, 32),
+}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference leg
+class CpuReference:
+    """The reference's CPU shard math (oracle port of the HF decoder layers the reference executes) on a bounded
+    sample: ``budget_layers`` of the model's layers at full width + the full-vocabulary lm_head, ``prompt``-token
+    prefill + a few decode tokens; layer time is scaled to the full depth.  All host threads."""
+
+    def __init__(self, cfg, rows, prompt, budget_layers, threads=None):
+        import torch
+        from oracle import shard_oracle as O
+        from tensorlink_b200.ml.weights import init_state_dict, synthetic_tokens
+        self.O, self.torch = O, torch
+        self.threads = threads or os.cpu_count()
+        torch.set_num_threads(self.threads)
+        self.cfg, self.rows, self.prompt, self.L = cfg, rows, prompt, budget_layers
+        self.sub = cfg.scaled(n_layers=budget_layers)
+        sd = init_state_dict(self.sub, dtype=torch.bfloat16, with_embed=False, with_head=True) if not cfg.tied else \
+            init_state_dict(self.sub, dtype=torch.bfloat16)
+        sd.setdefault("model.embed_tokens.weight", sd["lm_head.weight"])   # lookup cost is independent of the values
+        self.m = O.OracleModel(self.sub, sd, "sdpa_math")
+        self.ids = synthetic_tokens(cfg, rows, prompt)
+
+    def run(self, new, budget_new):
+        O, torch, sub, m = self.O, self.torch, self.sub, self.m
+        F = torch.nn.functional
+        rows, prompt, L = self.rows, self.prompt, self.L
+        with torch.no_grad():
+            cache = O.KVCache()
+            t0 = time.perf_counter()
+            x = F.embedding(self.ids, m.embed)
+            cos, sin = O.rope_tables(sub, torch.arange(prompt)[None].expand(rows, -1), x.dtype)
+            x = O.shard_forward(sub, m.layers, list(range(L)), x, cos, sin, "sdpa_math", cache)
+            t_prefill_layers = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            nxt = F.linear(O.rmsnorm(x[:, -1:], m.norm, sub.rms_eps), m.head)[:, -1].float().argmax(-1, keepdim=True)
+            t_head, t_layers = time.perf_counter() - t0, 0.0
+            for s in range(budget_new):
+                t0 = time.perf_counter()
+                x = F.embedding(nxt, m.embed)
+                cos, sin = O.rope_tables(sub, torch.full((rows, 1), prompt + s), x.dtype)
+                x = O.shard_forward(sub, m.layers, list(range(L)), x, cos, sin, "sdpa_math", cache)
+                t_layers += time.perf_counter() - t0
+                t0 = time.perf_counter()
+                nxt = F.linear(O.rmsnorm(x, m.norm, sub.rms_eps), m.head)[:, -1].float().argmax(-1, keepdim=True)
+                t_head += time.perf_counter() - t0
+        scale = self.cfg.n_layers / L
+        per_tok = (t_layers / budget_new) * scale + t_head / (budget_new + 1)
+        total = t_prefill_layers * scale + new * per_tok
+        sample = (f"oracle port (CPU bf16), {L} of {self.cfg.n_layers} layers at full width + full lm_head, rows={rows}, "
+                  f"prefill {prompt} + {budget_new} decode tokens measured, layer time scaled x{scale:.1f} to full depth "
+                  f"and extrapolated to a {new}-token generate")
+        return rows * new / total, sample
+
+
+# ------------------------------------------------------------------------------------------------ dominant kernel
+def measure_gemv_launches(dm, rows):
+    """CUDA-event duration of the weight-streaming GEMV launches of one decode step (eager, every layer touches its own
+    466 MB of weights, so nothing is L2-resident between launches).  Returns per-shape averages."""
+    import torch
+    from tensorlink_b200 import native as nat
+    st, cfg = dm.stage, dm.cfg
+    grp = st.slots[0]
+    v = st.params.v
+    w = grp._bufs(rows)
+    x = torch.randn(rows, cfg.hidden, device=dm.device).bfloat16()
+    shapes = {"qkv": (cfg.qkv_dim, cfg.hidden), "o": (cfg.hidden, cfg.q_dim), "gate_up": (2 * cfg.intermediate, cfg.hidden),
+              "down": (cfg.hidden, cfg.intermediate)}
+    acc = {k: [] for k in shapes}
+    for rep in range(3):
+        evs = []
+        for li in grp.layer_ids:
+            calls = (("qkv", lambda: nat.gemv(x, v[f"l{li}.wqkv"], out=w.qkv, bias=v.get(f"l{li}.bqkv"), norm_w=v[f"l{li}.ln1"], eps=cfg.rms_eps)),
+                     ("o", lambda: nat.gemv(w.attn, v[f"l{li}.wo"], out=x, residual=x)),
+                     ("gate_up", lambda: nat.gemv(x, v[f"l{li}.wgu"], out=w.act, norm_w=v[f"l{li}.ln2"], eps=cfg.rms_eps, flags=nat.EPI_SWIGLU)),
+                     ("down", lambda: nat.gemv(w.act, v[f"l{li}.wd"], out=x, residual=x)))
+            for name, fn in calls:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); fn(); e1.record()
+                evs.append((name, e0, e1))
+        torch.cuda.synchronize()
+        if rep:
+            for name, e0, e1 in evs:
+                acc[name].append(e0.elapsed_time(e1) * 1e-3)
+    out = {}
+    for k, (n, kk) in shapes.items():
+        t = sum(acc[k]) / max(1, len(acc[k]))
+        out[k] = {"bytes": 2 * n * kk, "s": t, "GBps": 2 * n * kk / t / 1e9 if t else None}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="qwen2.5-7b", choices=sorted(WORKLOADS))
+    ap.add_argument("--rows-per-gpu", type=int, default=1)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    name, prompt, new = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    N = max(args.gpus, 1)
+    rows = args.rows_per_gpu * N
+    from tensorlink_b200.ml.configs import get_config
+    cfg = get_config(name)
+    workload_desc = (f"{name} bf16 greedy generate, prompt {prompt} + {new} new tokens, global batch {rows} "
+                     f"({args.rows_per_gpu} row(s) per micro-batch x {N} micro-batches), {N} pipeline stage(s)")
+    base = {"metric": "generate tokens/sec", "unit": "tokens/s", "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_desc, "model": name, "global_batch": rows, "prompt_len": prompt,
+                       "new_tokens": new, "parallelism": f"pp{N}", "weights": "random-init (seeded, on device)",
+                       "l2": "inputs larger than L2: every decode step streams the stage's weights "
+                             f"({2 * cfg.total_params() / 1e9:.1f} GB total) from HBM"}}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        vals = []
+        ref = CpuReference(cfg, rows, prompt, budget_layers=1 if cfg.hidden > 2048 else 2)
+        cores, sample = ref.threads, ""
+        for i in range(args.warmup + args.steps):
+            v, sample = ref.run(new, budget_new=2 if i < args.warmup else 4)   # bounded sample per step
+            if i >= args.warmup:
+                vals.append(v)
+        val = sum(vals) / len(vals)
+        line = dict(base, impl="reference", value=val, ms_per_step=rows * new / val * 1e3,
+                    cpu_baseline={"value": val, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
+                    e2e={"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                    gpu_launches=0)
+        print(json.dumps(line), flush=True)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from tensorlink_b200.ml import DistributedModel
+    from tensorlink_b200.ml.weights import synthetic_tokens
+    from tensorlink_b200.p2p.link import init_process_group_from_env
+    if world > 1:
+        init_process_group_from_env("nccl")
+    else:
+        torch.cuda.set_device(0)
+    dm = DistributedModel(name, training=False, n_pipelines=N, max_batch=rows, max_seq=prompt + new + 8,
+                          init="device", max_tokens=args.rows_per_gpu * prompt)
+    ids_host = synthetic_tokens(cfg, rows, prompt).pin_memory()
+    ids_dev = ids_host.to(dm.device)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        out = dm.generate(ids_dev, max_new_tokens=new)
+    sync_all()
+    sampler = ClockSampler(torch.cuda.current_device())
+    if rank == 0:
+        sampler.start()
+    # ---- device-resident inputs
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        out = dm.generate(ids_dev, max_new_tokens=new)
+    e1.record()
+    sync_all()
+    t_dev = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dm.device)
+    # ---- end to end through the public API: pinned host ids in, host tokens out, every step
+    out_host = torch.empty(rows, prompt + new, dtype=torch.int64).pin_memory()
+    sync_all()
+    t0 = time.perf_counter()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        ids_in = ids_host.to(dm.device, non_blocking=True)
+        res = dm.generate(ids_in, max_new_tokens=new)
+        out_host.copy_(res, non_blocking=True)
+        torch.cuda.current_stream().synchronize()       # the caller holds the tokens on the host
+    e3.record()
+    sync_all()
+    t_e2e = torch.tensor([max(e2.elapsed_time(e3) * 1e-3, time.perf_counter() - t0)], device=dm.device)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    t_dev, t_e2e = float(t_dev), float(t_e2e)
+    toks = rows * new * args.steps
+
+    # ---- dominant kernel, live: the weight-streaming GEMV
+    hbm_peak, tf_peak, peak_kind = measured_peaks()
+    gv = measure_gemv_launches(dm, args.rows_per_gpu)
+    tot_b = sum(v["bytes"] for v in gv.values()); tot_s = sum(v["s"] for v in gv.values())
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(f"gemv_gate_up:{name}")
+    roof = {"bound": "hbm", "kernel": "tl::gemv_kernel (gate/up instantiation, SwiGLU epilogue)",
+            "achieved": gv["gate_up"]["GBps"], "peak": hbm_peak, "peak_kind": f"{peak_kind} copy bandwidth (burst)",
+            "unit": "GB/s", "frac": gv["gate_up"]["GBps"] / hbm_peak, "traffic": traffic,
+            "algorithmic_bytes_per_launch": gv["gate_up"]["bytes"], "launch_s": gv["gate_up"]["s"],
+            "all_gemv_launches": {"achieved": tot_b / tot_s / 1e9, "frac": tot_b / tot_s / 1e9 / hbm_peak,
+                                  "per_shape_GBps": {k: v["GBps"] for k, v in gv.items()}}}
+    # whole-step view: algorithmic HBM bytes of one decode token on this rank vs the time it took
+    n_local = len(dm.stage.slots[0].layer_ids)
+    step_bytes = 2 * n_local * cfg.layer_params() + (2 * cfg.vocab * cfg.hidden if dm.link.last else 0)
+    passes = args.steps * (new - 1) * N            # decode passes through this rank (one per micro-batch per token)
+    roof["decode_step"] = {"algorithmic_bytes_per_pass_this_rank": step_bytes,
+                           "achieved_GBps_whole_generate": step_bytes * passes / t_dev / 1e9,
+                           "note": "whole timed region incl. prefill, attention, launch gaps and pipeline bubbles"}
+    launches = args.steps * (new - 1) * N * dm.stage.n_decode_launches(args.rows_per_gpu)
+    line = dict(base, value=toks / t_dev, ms_per_step=t_dev / args.steps * 1e3,
+                e2e={"value": toks / t_e2e, "unit": "tokens/s", "h2d_bytes_per_step": rows * prompt * 8,
+                     "d2h_bytes_per_step": rows * (prompt + new) * 8},
+                gpu_launches=launches, clocks=clocks, roofline=roof)
+    if rank == 0:
+        if N == 1 and not args.no_cpu_baseline:
+            ref = CpuReference(cfg, rows, prompt, budget_layers=1 if cfg.hidden > 2048 else 2)
+            ref.run(new, 1)
+            v, sample = ref.run(new, 4)
+            line["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": ref.threads, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

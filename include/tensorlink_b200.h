@@ -107,6 +107,9 @@ int tl_argmax_bf16(const void* logits, int64_t* ids_out, void* workspace, size_t
 
 /* ---- small device-side helpers used by the captured decode graph */
 int tl_advance_pos(int32_t* pos_dev, int32_t* kv_len_dev, int delta, void* stream); /* pos += delta; kv_len = pos */
+/* out_tokens[b, *step_dev] = ids[b] for b < B (row pitch ld), then ++*step_dev: the generated-token log
+ * (replaces the per-token TOKEN packet, tensorlink/p2p/torch_node.py:543-551) */
+int tl_append_token(const int64_t* ids, int64_t* out_tokens, int32_t* step_dev, int B, int ld, void* stream);
 
 #ifdef __cplusplus
 }

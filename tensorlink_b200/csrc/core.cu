@@ -44,6 +44,14 @@ __global__ void advance_pos_kernel(int32_t* pos, int32_t* kv_len, int delta) {
     if (kv_len) *kv_len = p;
 }
 
+// out_tokens[b, *step] = ids[b]; then ++*step  (one thread block, B <= 1024)
+__global__ void append_token_kernel(const int64_t* ids, int64_t* out_tokens, int32_t* step, int B, int ld) {
+    const int s = *step;
+    __syncthreads();
+    if ((int)threadIdx.x < B && s < ld) out_tokens[(size_t)threadIdx.x * ld + s] = ids[threadIdx.x];
+    if (threadIdx.x == 0) *step = s + 1;
+}
+
 }  // namespace tl
 
 extern "C" {
@@ -80,6 +88,12 @@ int tl_advance_pos(int32_t* pos_dev, int32_t* kv_len_dev, int delta, void* strea
     TL_REQUIRE(pos_dev != nullptr, TL_ERR_INVALID, "tl_advance_pos: null pos");
     tl::advance_pos_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(pos_dev, kv_len_dev, delta);
     return tl::check_launch("tl_advance_pos");
+}
+
+int tl_append_token(const int64_t* ids, int64_t* out_tokens, int32_t* step_dev, int B, int ld, void* stream) {
+    TL_REQUIRE(ids && out_tokens && step_dev && B >= 1 && B <= 1024, TL_ERR_INVALID, "tl_append_token: bad args");
+    tl::append_token_kernel<<<1, ((B + 31) / 32) * 32, 0, (cudaStream_t)stream>>>(ids, out_tokens, step_dev, B, ld);
+    return tl::check_launch("tl_append_token");
 }
 
 }  // extern "C"

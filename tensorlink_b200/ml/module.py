@@ -1,0 +1,260 @@
+"""``DistributedModel`` — the reference's user-facing front end, driving B200 pipeline stages.
+
+Mirrors /root/reference/tensorlink/ml/module.py: constructor signature (:251-265), ``forward`` returning an HF-style
+output with ``.logits`` / ``.loss`` (:348-407), ``generate`` (:763-769), ``create_optimizer`` (:1016-1021),
+``train/eval`` (:534-566), ``parameters`` (:577-650), ``distribute_model(config)`` (:699).  The reference is
+hub-and-spoke: the user process RPCs each worker in turn over TCP and polls.  Here every pipeline stage is one
+process on one GPU (``torchrun``), all of them construct the same ``DistributedModel`` (SPMD) and activations
+go stage -> stage directly over NVLink (p2p/link.py).  With one process the whole model is a single stage.
+
+Documented deviations from the reference: errors raise instead of being swallowed into ``{"error": ...}`` dicts
+(module.py:978-985); ``dtype`` defaults to bf16 (the only dtype the sm_100a kernels implement); logits live on
+the last stage (pass ``gather_logits=True`` to copy them to rank 0).
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass
+from typing import Any, Callable, Dict, List, Optional, Union
+
+import torch
+
+from ..p2p.link import StageLink, init_process_group_from_env
+from . import graphing
+from .configs import ShardModelConfig, get_config
+
+
+@dataclass
+class CausalLMOutput:
+    """The two fields of HF ``CausalLMOutputWithPast`` the reference's callers read."""
+    loss: Optional[torch.Tensor] = None
+    logits: Optional[torch.Tensor] = None
+
+    def __getitem__(self, k):
+        return getattr(self, k)
+
+
+def _default_stage_factory(**kw):
+    from .stage import CudaStage          # imports the CUDA library; raises without it
+    return CudaStage(**kw)
+
+
+def _config_from_hf(model) -> ShardModelConfig:
+    c = model.config
+    qk_norm = c.__class__.__name__.startswith("Qwen3")
+    hd = getattr(c, "head_dim", None) or c.hidden_size // c.num_attention_heads
+    rp = getattr(c, "rope_parameters", None) or {}
+    theta = rp.get("rope_theta", getattr(c, "rope_theta", 1e6))
+    return ShardModelConfig(getattr(c, "name_or_path", "") or c.__class__.__name__, c.hidden_size,
+                            c.intermediate_size, c.num_hidden_layers, c.num_attention_heads,
+                            c.num_key_value_heads, hd, c.vocab_size, tied=bool(c.tie_word_embeddings),
+                            qkv_bias=not qk_norm, qk_norm=qk_norm, rope_theta=float(theta),
+                            rms_eps=float(c.rms_norm_eps), max_pos=int(c.max_position_embeddings))
+
+
+class DistributedModel(torch.nn.Module):
+    def __init__(self, model: Union[torch.nn.Module, str, ShardModelConfig], n_pipelines: int = 1,
+                 optimizer=None, scheduler_type=None, device: Optional[str] = None,
+                 dtype: torch.dtype = torch.bfloat16, trusted: bool = False, node: Optional[Any] = None,
+                 training: bool = True, verbose: bool = False, tokenizer=None, config: Optional[dict] = None,
+                 *, max_batch: int = 8, max_seq: int = 4096, seed: int = 1234, init: str = "seeded",
+                 balanced_plan: bool = False, link: Optional[StageLink] = None, max_tokens: Optional[int] = None,
+                 _stage_factory: Optional[Callable] = None):
+        super().__init__()
+        if dtype != torch.bfloat16:
+            raise NotImplementedError("tensorlink_b200 computes in bf16 with fp32 accumulation; pass dtype=torch.bfloat16")
+        state_dict = None
+        if isinstance(model, torch.nn.Module):
+            self.cfg = _config_from_hf(model)
+            state_dict = model.state_dict()
+        elif isinstance(model, ShardModelConfig):
+            self.cfg = model
+        else:
+            self.cfg = get_config(model)
+        self.model_name = self.cfg.name
+        self.name = self.model_name
+        self.tokenizer = tokenizer
+        self.n_pipelines = max(1, int(n_pipelines))          # micro-batches in flight (module.py:374-399)
+        self.n_datalines = 1
+        self.optimizer = optimizer
+        self.scheduler = scheduler_type
+        self.training = training
+        self.verbose = verbose
+        self.trusted = trusted
+        self.job_id = None
+        if node is None:
+            from ..nodes.nodes import User
+            node = User()
+        self.node = node
+        self.node_requests = getattr(node, "node_requests", None)
+        self.node_responses = getattr(node, "node_responses", None)
+        self.mpc_lock = getattr(node, "mpc_lock", None)
+
+        if link is None:
+            init_process_group_from_env()
+            link = StageLink.from_env()
+        self.link = link
+        self.rank, self.world = link.rank, link.world
+        if device is None:
+            device = f"cuda:{torch.cuda.current_device()}" if torch.cuda.is_available() else "cpu"
+        self.device = torch.device(device)
+
+        self.config = config if config else {}
+        self.max_batch, self.max_seq, self.seed = max_batch, max_seq, seed
+        self._stage_factory = _stage_factory or _default_stage_factory
+        self._stage_kw = dict(init=init, state_dict=state_dict, balanced=balanced_plan, max_tokens=max_tokens)
+        self.distributed_graph: Dict[str, Any] = {}
+        self.stage = None
+        self.timers: Dict[str, float] = {}
+        if self.node.__class__.__name__ == "User":
+            self._initialize_distribution()
+
+    # ------------------------------------------------------------------------------------------ distribution
+    def _initialize_distribution(self):
+        """module.py:987-1021: obtain a plan, distribute, expose ``create_optimizer``."""
+        plan = self.config or graphing.make_plan(self.cfg, self.world, self.training, self._stage_kw["balanced"])
+        self.distribute_model(plan)
+
+    def distribute_model(self, config: Optional[dict] = None):
+        """module.py:699-761.  Every rank materialises exactly its entries of the plan."""
+        plan = config or self.config or graphing.make_plan(self.cfg, self.world, self.training)
+        if graphing.n_stages(plan) != self.world:
+            raise ValueError(f"plan has {graphing.n_stages(plan)} stages but the job has {self.world} ranks")
+        self.distributed_graph = plan
+        layers = graphing.stage_layers(plan, self.rank)
+        n_slots = self.n_pipelines
+        per_slot = (self.max_batch + n_slots - 1) // n_slots
+        self.stage = self._stage_factory(cfg=self.cfg, layer_ids=layers, has_embed=self.rank == 0,
+                                         has_head=self.rank == self.world - 1, device=self.device,
+                                         max_batch=per_slot, max_seq=self.max_seq, n_slots=n_slots,
+                                         training=self.training, state_dict=self._stage_kw["state_dict"],
+                                         seed=self.seed, init=self._stage_kw["init"],
+                                         max_tokens=self._stage_kw["max_tokens"])
+        self._stage_kw["state_dict"] = None
+        return plan
+
+    # ------------------------------------------------------------------------------------------ nn.Module surface
+    def train(self, mode: bool = True):
+        self.training = mode
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+    def parameters(self, recurse: bool = True, distributed: bool = True, load: bool = True):
+        """module.py:577-650: this rank's parameters under their HF names (values, not nn.Parameters)."""
+        return iter(self.stage.params.hf_state_dict().values())
+
+    def state_dict(self, *a, **k):
+        return self.stage.params.hf_state_dict()
+
+    def create_optimizer(self, **optimizer_kwargs):
+        from .optim import create_distributed_optimizer
+        return create_distributed_optimizer(self, self.optimizer, **optimizer_kwargs)
+
+    # ------------------------------------------------------------------------------------------ forward
+    def forward(self, *args, **kwargs) -> CausalLMOutput:
+        """One forward through every stage (module.py:348-407).  ``input_ids`` positional or keyword (:355-359).
+        Inference: logits [B,S,V] on the last stage.  Training (``self.training`` with a grad-enabled stage):
+        handled by ``ml/train.py``."""
+        input_ids = kwargs.pop("input_ids", args[0] if args else None)
+        labels = kwargs.pop("labels", None)
+        gather = kwargs.pop("gather_logits", False)
+        if self.training and getattr(self.stage, "supports_training", False):
+            from .train import train_forward
+            return train_forward(self, input_ids, labels)
+        return self._infer_forward(input_ids, gather)
+
+    def _infer_forward(self, input_ids: Optional[torch.Tensor], gather: bool) -> CausalLMOutput:
+        link, st, cfg = self.link, self.stage, self.cfg
+        shape = link.broadcast_object(tuple(input_ids.shape) if link.first else None)
+        B, S = shape
+        if link.first:
+            x = st.embed(input_ids.to(self.device))
+        else:
+            x = torch.empty(B, S, cfg.hidden, dtype=torch.bfloat16, device=self.device)
+            link.recv(x, link.prev)
+        x = st.prefill(x, 0, 0)
+        if not link.last:
+            link.send(x.contiguous(), link.next)
+            logits = None
+        else:
+            logits = st.head_logits(x.reshape(B * S, cfg.hidden)).view(B, S, cfg.vocab)
+        if gather and self.world > 1:
+            if link.last:
+                link.send(logits.contiguous(), 0)
+            elif link.first:
+                logits = torch.empty(B, S, cfg.vocab, dtype=torch.bfloat16, device=self.device)
+                link.recv(logits, self.world - 1)
+        return CausalLMOutput(logits=logits)
+
+    # ------------------------------------------------------------------------------------------ generate
+    @torch.no_grad()
+    def generate(self, *args, **kwargs) -> Optional[torch.Tensor]:
+        """Greedy generation (module.py:763-769 delegates to HF ``generate``; only ``do_sample=False`` is
+        implemented).  ``input_ids`` [B,S] int64 on the first stage; returns [B,S+new] on every rank.
+        ``streamer``: object with ``put(tensor)`` / ``end()`` (HF BaseStreamer protocol), called on rank 0
+        with each new token column, all batch rows (the reference streams row 0 only, worker.py:134-139)."""
+        input_ids = kwargs.pop("input_ids", args[0] if args else None)
+        max_new = int(kwargs.pop("max_new_tokens", 20))
+        streamer = kwargs.pop("streamer", None)
+        use_graph = kwargs.pop("use_graph", True)
+        if kwargs.pop("do_sample", False):
+            raise NotImplementedError("sampling is not implemented; generate() is greedy (do_sample=False)")
+        kwargs.pop("eos_token_id", None); kwargs.pop("pad_token_id", None)
+        link, st, cfg = self.link, self.stage, self.cfg
+        shape = link.broadcast_object(tuple(input_ids.shape) if link.first else None)
+        B, S = shape
+        n_mb = min(self.n_pipelines, B)
+        if B % n_mb:
+            raise ValueError(f"batch {B} not divisible into {n_mb} micro-batches")
+        b = B // n_mb
+        if b > st.max_batch or S + max_new > st.max_seq:
+            raise ValueError(f"stage sized for micro-batch<={st.max_batch}, T<={st.max_seq}; got {b}, {S + max_new}")
+        dev = self.device
+        t0 = time.perf_counter()
+        out_tokens = torch.zeros(B, max_new, dtype=torch.int64, device=dev) if link.first else None
+        ids_rows = [input_ids[m * b:(m + 1) * b].to(dev) for m in range(n_mb)] if link.first else [None] * n_mb
+
+        # ---- prefill every micro-batch through the pipeline; the last stage produces the first new token
+        xbuf = [torch.empty(b, S, cfg.hidden, dtype=torch.bfloat16, device=dev) for _ in range(n_mb)] \
+            if not link.first else None
+        for m in range(n_mb):
+            x = st.embed(ids_rows[m]) if link.first else xbuf[m]
+            if not link.first:
+                link.recv(x, link.prev)
+            x = st.prefill(x, 0, m)
+            if not link.last:
+                link.send(x.contiguous(), link.next)
+            else:
+                st.head_argmax(x[:, -1, :].contiguous(), st.ids_dec[m][:b])
+                if self.world > 1:
+                    link.send(st.ids_dec[m][:b], 0)
+        # ---- decode rounds: micro-batches rotate through the stages; hidden [b,H] hops forward, ids hop back
+        for step in range(max_new):
+            for m in range(n_mb):
+                if link.first:
+                    if self.world > 1:
+                        link.recv(st.ids_dec[m][:b], self.world - 1)
+                    out_tokens[m * b:(m + 1) * b, step] = st.ids_dec[m][:b]
+                    if streamer is not None and n_mb == 1:
+                        streamer.put(st.ids_dec[m][:b].cpu())
+                if step == max_new - 1:
+                    continue
+                if not link.first:
+                    link.recv(st.x_dec[m][:b], link.prev)
+                st.decode(m, b, use_graph)
+                if not link.last:
+                    link.send(st.x_dec[m][:b], link.next)
+                elif self.world > 1:
+                    link.send(st.ids_dec[m][:b], 0)
+        if link.first:
+            result = torch.cat([input_ids.to(dev), out_tokens], dim=1)
+        else:
+            result = torch.empty(B, S + max_new, dtype=torch.int64, device=dev)
+        if self.world > 1:
+            torch.distributed.broadcast(result, src=0, group=link.group)
+        if streamer is not None and link.first:
+            streamer.end()
+        self.timers["generate_wall_s"] = time.perf_counter() - t0
+        return result

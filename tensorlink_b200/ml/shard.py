@@ -1,0 +1,306 @@
+"""The CUDA shard operator: a contiguous layer range executed by the sm_100a kernels.
+
+Mirrors the reference's shard operator ``LayerGroupModule`` (/root/reference/tensorlink/ml/injector.py:154-281):
+same constructor role (a list of layers + the loop live-ins), ``num_layers`` attribute, ``forward(**kwargs) ->
+dict`` returning ``kwargs ∪ {hidden_states}``.  What differs is everything underneath: instead of ``exec``-ing
+HF's loop body over ``nn.Module`` layers, each layer is five to eight kernel launches on a resident bf16
+parameter arena with a resident KV cache; masks, RoPE tables and positions are generated on the device and
+never cross a shard boundary (the reference ships them with every call, injector.py:508-556).
+
+HBM layout (per shard):
+  params   one flat bf16 arena; per layer  ln1 | wqkv[(n_h+2n_kv)d, H] | bqkv | (q_norm,k_norm) | wo[H, n_h d] |
+           ln2 | wgu[2I, H] (row 2j = gate_j, row 2j+1 = up_j) | wd[H, I]; then embed / final norm / lm_head
+           on the ranks that own them.  Every tensor starts on a 256-byte boundary (TMA needs 16).
+  kv       per layer K and V  [B_max, n_kv, T_max, d] bf16 (head-major: decode streams [T, d] per head).
+  act      x[N,H], qkv[N,(n_h+2n_kv)d], q[N,n_h d], attn[N,n_h d], h[N,H], act[N,I]  for N = B*S tokens.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Iterable, List, Optional, Sequence
+
+import torch
+
+from .. import native as nat
+from .configs import ShardModelConfig
+from .weights import init_state_dict
+
+ALIGN = 128  # elements (256 B)
+
+
+def _rope_inv_freq(cfg: ShardModelConfig) -> torch.Tensor:
+    """site-packages/transformers/models/qwen2/modeling_qwen2.py:84-99, computed on the host in fp32 like HF."""
+    d = cfg.head_dim
+    return 1.0 / (cfg.rope_theta ** (torch.arange(0, d, 2, dtype=torch.int64).to(torch.float32) / d))
+
+
+class ShardParams:
+    """Flat bf16 parameter arena of one shard, with fused-QKV / interleaved gate-up views."""
+
+    def __init__(self, cfg: ShardModelConfig, layer_ids: Sequence[int], has_embed: bool, has_head: bool,
+                 device, with_grad: bool = False):
+        self.cfg, self.layer_ids = cfg, list(layer_ids)
+        self.has_embed, self.has_head = has_embed, has_head
+        self.device = torch.device(device)
+        H, I = cfg.hidden, cfg.intermediate
+        spec: List[tuple] = []
+        for li in self.layer_ids:
+            spec += [(f"l{li}.ln1", (H,)), (f"l{li}.wqkv", (cfg.qkv_dim, H))]
+            if cfg.qkv_bias:
+                spec.append((f"l{li}.bqkv", (cfg.qkv_dim,)))
+            if cfg.qk_norm:
+                spec += [(f"l{li}.qn", (cfg.head_dim,)), (f"l{li}.kn", (cfg.head_dim,))]
+            spec += [(f"l{li}.wo", (H, cfg.q_dim)), (f"l{li}.ln2", (H,)), (f"l{li}.wgu", (2 * I, H)),
+                     (f"l{li}.wd", (H, I))]
+        if has_embed:
+            spec.append(("embed", (cfg.vocab, H)))
+        if has_head:
+            spec.append(("norm", (H,)))
+            if not (cfg.tied and has_embed):
+                spec.append(("head", (cfg.vocab, H)))
+        self.spec = spec
+        self.offsets: Dict[str, tuple] = {}
+        off = 0
+        for name, shape in spec:
+            n = 1
+            for s in shape:
+                n *= s
+            self.offsets[name] = (off, n, shape)
+            off += (n + ALIGN - 1) // ALIGN * ALIGN
+        self.numel = off
+        self.flat = torch.zeros(off, dtype=torch.bfloat16, device=self.device)
+        self.grad: Optional[torch.Tensor] = torch.zeros_like(self.flat) if with_grad else None
+        self.v: Dict[str, torch.Tensor] = {n: self.flat[o:o + k].view(shape) for n, (o, k, shape) in self.offsets.items()}
+        self.g: Dict[str, torch.Tensor] = ({n: self.grad[o:o + k].view(shape) for n, (o, k, shape) in self.offsets.items()}
+                                           if with_grad else {})
+        if has_head and cfg.tied and has_embed:
+            self.v["head"] = self.v["embed"]
+            if with_grad:
+                self.g["head"] = self.g["embed"]
+
+    # ---- HF state dict  <->  fused layout ------------------------------------------------------------
+    def load_hf_state_dict(self, sd: Dict[str, torch.Tensor]):
+        """Fuse q/k/v, interleave gate/up (the role of worker.py:542-638 ``_load_grouped_layer_weights``)."""
+        cfg = self.cfg
+        dev = self.device
+
+        def put(name, t):
+            self.v[name].copy_(t.to(device=dev, dtype=torch.bfloat16))
+
+        for li in self.layer_ids:
+            p = f"model.layers.{li}."
+            put(f"l{li}.ln1", sd[p + "input_layernorm.weight"])
+            put(f"l{li}.wqkv", torch.cat([sd[p + "self_attn.q_proj.weight"], sd[p + "self_attn.k_proj.weight"],
+                                          sd[p + "self_attn.v_proj.weight"]], dim=0))
+            if cfg.qkv_bias:
+                put(f"l{li}.bqkv", torch.cat([sd[p + "self_attn.q_proj.bias"], sd[p + "self_attn.k_proj.bias"],
+                                              sd[p + "self_attn.v_proj.bias"]], dim=0))
+            if cfg.qk_norm:
+                put(f"l{li}.qn", sd[p + "self_attn.q_norm.weight"])
+                put(f"l{li}.kn", sd[p + "self_attn.k_norm.weight"])
+            put(f"l{li}.wo", sd[p + "self_attn.o_proj.weight"])
+            put(f"l{li}.ln2", sd[p + "post_attention_layernorm.weight"])
+            g, u = sd[p + "mlp.gate_proj.weight"], sd[p + "mlp.up_proj.weight"]
+            put(f"l{li}.wgu", torch.stack([g, u], dim=1).reshape(2 * cfg.intermediate, cfg.hidden))
+            put(f"l{li}.wd", sd[p + "mlp.down_proj.weight"])
+        if self.has_embed:
+            put("embed", sd["model.embed_tokens.weight"])
+        if self.has_head:
+            put("norm", sd["model.norm.weight"])
+            if not (cfg.tied and self.has_embed):
+                put("head", sd["lm_head.weight"] if "lm_head.weight" in sd else sd["model.embed_tokens.weight"])
+
+    def hf_state_dict(self, grads: bool = False) -> Dict[str, torch.Tensor]:
+        """Inverse mapping (the role of ``parameters(distributed=True)``, module.py:577-650)."""
+        cfg = self.cfg
+        src = self.g if grads else self.v
+        out: Dict[str, torch.Tensor] = {}
+        for li in self.layer_ids:
+            p = f"model.layers.{li}."
+            out[p + "input_layernorm.weight"] = src[f"l{li}.ln1"].clone()
+            q, k, v = src[f"l{li}.wqkv"].split([cfg.q_dim, cfg.kv_dim, cfg.kv_dim], dim=0)
+            out[p + "self_attn.q_proj.weight"], out[p + "self_attn.k_proj.weight"] = q.clone(), k.clone()
+            out[p + "self_attn.v_proj.weight"] = v.clone()
+            if cfg.qkv_bias:
+                bq, bk, bv = src[f"l{li}.bqkv"].split([cfg.q_dim, cfg.kv_dim, cfg.kv_dim], dim=0)
+                out[p + "self_attn.q_proj.bias"], out[p + "self_attn.k_proj.bias"] = bq.clone(), bk.clone()
+                out[p + "self_attn.v_proj.bias"] = bv.clone()
+            if cfg.qk_norm:
+                out[p + "self_attn.q_norm.weight"] = src[f"l{li}.qn"].clone()
+                out[p + "self_attn.k_norm.weight"] = src[f"l{li}.kn"].clone()
+            out[p + "self_attn.o_proj.weight"] = src[f"l{li}.wo"].clone()
+            out[p + "post_attention_layernorm.weight"] = src[f"l{li}.ln2"].clone()
+            gu = src[f"l{li}.wgu"].view(cfg.intermediate, 2, cfg.hidden)
+            out[p + "mlp.gate_proj.weight"], out[p + "mlp.up_proj.weight"] = gu[:, 0].clone(), gu[:, 1].clone()
+            out[p + "mlp.down_proj.weight"] = src[f"l{li}.wd"].clone()
+        if self.has_embed:
+            out["model.embed_tokens.weight"] = src["embed"].clone()
+        if self.has_head:
+            out["model.norm.weight"] = src["norm"].clone()
+            if not (cfg.tied and self.has_embed):
+                out["lm_head.weight"] = src["head"].clone()
+        return out
+
+    def init_seeded(self, seed: int = 1234):
+        """Same values the CPU oracle draws (weights.init_state_dict), materialised layer by layer."""
+        cfg = self.cfg
+        for li in self.layer_ids:
+            sd = init_state_dict(cfg, seed, torch.bfloat16, "cpu", layers=[li], with_embed=False, with_head=False)
+            sub = ShardParams.__new__(ShardParams)
+            sub.__dict__.update(self.__dict__)
+            sub.layer_ids, sub.has_embed, sub.has_head = [li], False, False
+            sub.load_hf_state_dict(sd)
+        sd = init_state_dict(cfg, seed, torch.bfloat16, "cpu", layers=[], with_embed=self.has_embed or (
+            self.has_head and cfg.tied), with_head=self.has_head)
+        sub = ShardParams.__new__(ShardParams)
+        sub.__dict__.update(self.__dict__)
+        sub.layer_ids = []
+        sub.load_hf_state_dict(sd)
+
+    def init_on_device(self, seed: int = 1234, std: float = 0.02):
+        """Random init drawn directly on the GPU (benchmarks at 7B/8B scale; not comparable with the oracle)."""
+        g = torch.Generator(device=self.device).manual_seed(seed)
+        self.flat.normal_(0.0, std, generator=g)
+        for name in self.v:
+            if name.endswith(("ln1", "ln2", "qn", "kn")) or name == "norm":
+                self.v[name].fill_(1.0)
+
+
+@dataclass
+class ShardBuffers:
+    """Activation workspaces for up to ``n_max`` tokens in flight."""
+    x: torch.Tensor
+    h: torch.Tensor
+    qkv: torch.Tensor
+    q: torch.Tensor
+    attn: torch.Tensor
+    act: torch.Tensor
+
+
+class CudaLayerGroup:
+    """B200 shard operator (LayerGroupModule mirror, injector.py:154-281)."""
+
+    def __init__(self, cfg: ShardModelConfig, params: ShardParams, max_batch: int, max_seq: int,
+                 max_tokens: Optional[int] = None):
+        nat.require_device()
+        self.cfg, self.p = cfg, params
+        self.layer_ids = params.layer_ids
+        self.num_layers = len(self.layer_ids)             # worker.py:332-335 dispatches on this attribute
+        self.input_vars = ["hidden_states", "past_len", "use_cache"]
+        self.output_vars = ["hidden_states"]
+        self.device = params.device
+        self.B_max, self.T_max = max_batch, max_seq
+        dev, bf = self.device, torch.bfloat16
+        self.kc = [torch.zeros(max_batch, cfg.n_kv_heads, max_seq, cfg.head_dim, dtype=bf, device=dev)
+                   for _ in self.layer_ids]
+        self.vc = [torch.zeros_like(k) for k in self.kc]
+        self.cos, self.sin = nat.rope_table(_rope_inv_freq(cfg).to(dev), max_seq)
+        self.pos_dev = torch.zeros(1, dtype=torch.int32, device=dev)      # next write position in the cache
+        self.kvlen_dev = torch.zeros(1, dtype=torch.int32, device=dev)    # valid keys for the decode kernel
+        self.n_max = max_tokens or max_batch * max_seq
+        self._alloc_bufs(min(self.n_max, 8))
+        self.dec_ws = torch.empty(max(nat.attn_decode_ws(max_batch, cfg.n_heads, cfg.head_dim, max_seq), 16),
+                                  dtype=torch.uint8, device=dev)
+        self.scale = cfg.head_dim ** -0.5
+
+    def _alloc_bufs(self, n: int):
+        cfg, dev, bf = self.cfg, self.device, torch.bfloat16
+        self.bufs = ShardBuffers(
+            x=torch.empty(n, cfg.hidden, dtype=bf, device=dev), h=torch.empty(n, cfg.hidden, dtype=bf, device=dev),
+            qkv=torch.empty(n, cfg.qkv_dim, dtype=bf, device=dev), q=torch.empty(n, cfg.q_dim, dtype=bf, device=dev),
+            attn=torch.empty(n, cfg.q_dim, dtype=bf, device=dev),
+            act=torch.empty(n, cfg.intermediate, dtype=bf, device=dev))
+        self.n_alloc = n
+
+    def _bufs(self, n: int) -> ShardBuffers:
+        if n > self.n_alloc:
+            self._alloc_bufs(n)
+        b = self.bufs
+        return ShardBuffers(b.x[:n], b.h[:n], b.qkv[:n], b.q[:n], b.attn[:n], b.act[:n])
+
+    # ------------------------------------------------------------------------------------------ cache control
+    def reset_cache(self, past_len: int = 0):
+        self.pos_dev.fill_(past_len)
+        self.kvlen_dev.fill_(past_len)
+
+    # ------------------------------------------------------------------------------------------ layer bodies
+    def _layer_prefill(self, j: int, x: torch.Tensor, B: int, S: int, past_len: int, w: ShardBuffers):
+        """site-packages/transformers/models/qwen2/modeling_qwen2.py:280-310 for N = B*S tokens (GEMM path)."""
+        cfg, v, li = self.cfg, self.p.v, self.layer_ids[j]
+        nat.rmsnorm_fwd(x, v[f"l{li}.ln1"], cfg.rms_eps, out=w.h)
+        nat.gemm(w.h, v[f"l{li}.wqkv"], out=w.qkv, bias=v.get(f"l{li}.bqkv"))
+        nat.rope_kv_fwd(w.qkv, w.q, self.kc[j], self.vc[j], self.pos_dev, self.cos, self.sin, v.get(f"l{li}.qn"),
+                        v.get(f"l{li}.kn"), cfg.rms_eps, S, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim)
+        nat.attn_prefill_fwd(w.q, self.kc[j], self.vc[j], w.attn, None, B, S, past_len, cfg.n_heads, cfg.n_kv_heads,
+                             cfg.head_dim, self.scale)
+        nat.gemm(w.attn, v[f"l{li}.wo"], out=x, residual=x)
+        nat.rmsnorm_fwd(x, v[f"l{li}.ln2"], cfg.rms_eps, out=w.h)
+        nat.gemm(w.h, v[f"l{li}.wgu"], out=w.act, flags=nat.EPI_SWIGLU)
+        nat.gemm(w.act, v[f"l{li}.wd"], out=x, residual=x)
+
+    def _layer_decode(self, j: int, x: torch.Tensor, B: int, w: ShardBuffers):
+        """Same layer for B <= 8 single-token rows: weight-streaming GEMVs with the norms fused as prologues."""
+        cfg, v, li = self.cfg, self.p.v, self.layer_ids[j]
+        nat.gemv(x, v[f"l{li}.wqkv"], out=w.qkv, bias=v.get(f"l{li}.bqkv"), norm_w=v[f"l{li}.ln1"], eps=cfg.rms_eps)
+        nat.rope_kv_fwd(w.qkv, w.q, self.kc[j], self.vc[j], self.pos_dev, self.cos, self.sin, v.get(f"l{li}.qn"),
+                        v.get(f"l{li}.kn"), cfg.rms_eps, 1, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim)
+        nat.attn_decode_fwd(w.q, self.kc[j], self.vc[j], w.attn, self.kvlen_dev, self.dec_ws, B, cfg.n_heads,
+                            cfg.n_kv_heads, cfg.head_dim, self.scale)
+        nat.gemv(w.attn, v[f"l{li}.wo"], out=x, residual=x)
+        nat.gemv(x, v[f"l{li}.wgu"], out=w.act, norm_w=v[f"l{li}.ln2"], eps=cfg.rms_eps, flags=nat.EPI_SWIGLU)
+        nat.gemv(w.act, v[f"l{li}.wd"], out=x, residual=x)
+
+    def _layer_decode_batched(self, j: int, x: torch.Tensor, B: int, w: ShardBuffers):
+        """B > 8 single-token rows: tcgen05 GEMMs (weights streamed once per step) + split-KV decode attention."""
+        cfg, v, li = self.cfg, self.p.v, self.layer_ids[j]
+        nat.rmsnorm_fwd(x, v[f"l{li}.ln1"], cfg.rms_eps, out=w.h)
+        nat.gemm(w.h, v[f"l{li}.wqkv"], out=w.qkv, bias=v.get(f"l{li}.bqkv"))
+        nat.rope_kv_fwd(w.qkv, w.q, self.kc[j], self.vc[j], self.pos_dev, self.cos, self.sin, v.get(f"l{li}.qn"),
+                        v.get(f"l{li}.kn"), cfg.rms_eps, 1, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim)
+        nat.attn_decode_fwd(w.q, self.kc[j], self.vc[j], w.attn, self.kvlen_dev, self.dec_ws, B, cfg.n_heads,
+                            cfg.n_kv_heads, cfg.head_dim, self.scale)
+        nat.gemm(w.attn, v[f"l{li}.wo"], out=x, residual=x)
+        nat.rmsnorm_fwd(x, v[f"l{li}.ln2"], cfg.rms_eps, out=w.h)
+        nat.gemm(w.h, v[f"l{li}.wgu"], out=w.act, flags=nat.EPI_SWIGLU)
+        nat.gemm(w.act, v[f"l{li}.wd"], out=x, residual=x)
+
+    # ------------------------------------------------------------------------------------------ shard passes
+    def prefill(self, hidden: torch.Tensor, past_len: int = 0) -> torch.Tensor:
+        """hidden [B,S,H] -> [B,S,H]; appends S positions to the KV cache starting at ``past_len``."""
+        B, S, H = hidden.shape
+        if B > self.B_max or past_len + S > self.T_max:
+            raise ValueError(f"shard sized for B<={self.B_max}, T<={self.T_max}; got B={B}, T={past_len + S}")
+        N = B * S
+        w = self._bufs(N)
+        w.x.copy_(hidden.reshape(N, H))
+        self.pos_dev.fill_(past_len)
+        for j in range(self.num_layers):
+            self._layer_prefill(j, w.x, B, S, past_len, w)
+        self.pos_dev.fill_(past_len + S)
+        self.kvlen_dev.fill_(past_len + S)
+        return w.x.view(B, S, H)
+
+    def decode_step_inplace(self, x: torch.Tensor):
+        """x [B,H] updated in place through this shard's layers; one new token per row at position ``pos_dev``.
+        Graph-capturable: the write position and the KV length live in device memory and are advanced by
+        kernels inside the same launch sequence (kv_len += 1 before the layers, pos += 1 after)."""
+        B = x.shape[0]
+        w = self._bufs(B)
+        nat.advance_pos(self.kvlen_dev, None, 1)
+        for j in range(self.num_layers):
+            if B <= 8:
+                self._layer_decode(j, x, B, w)
+            else:
+                self._layer_decode_batched(j, x, B, w)
+        nat.advance_pos(self.pos_dev, None, 1)
+
+    # ------------------------------------------------------------------------------------------ reference-shaped API
+    def forward(self, **kwargs) -> dict:
+        """``LayerGroupModule.forward`` contract (injector.py:252-260): returns kwargs ∪ outputs."""
+        hs = kwargs["hidden_states"]
+        past_len = int(kwargs.get("past_len", 0) or 0)
+        out = dict(kwargs)
+        out["hidden_states"] = self.prefill(hs, past_len).clone()
+        return out
+
+    __call__ = forward

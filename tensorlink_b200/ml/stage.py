@@ -1,0 +1,121 @@
+"""One pipeline stage on one B200: parameters + per-micro-batch shard operators + captured decode graphs.
+
+This is the worker half of the reference's hot path (/root/reference/tensorlink/ml/worker.py):
+``load_module`` (:452-505) -> ``CudaStage.__init__``; ``_handle_forward`` (:297-357) -> ``prefill`` / ``decode``;
+``_handle_generate`` (:359-441) -> the decode graph.  There is no polling loop and no IPC: the stage is driven
+in-process by ``DistributedModel`` and neighbours are reached through ``StageLink``.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from .. import native as nat
+from .configs import ShardModelConfig
+from .shard import CudaLayerGroup, ShardParams
+
+
+class CudaStage:
+    def __init__(self, cfg: ShardModelConfig, layer_ids, has_embed: bool, has_head: bool, device,
+                 max_batch: int, max_seq: int, n_slots: int = 1, training: bool = False,
+                 state_dict: Optional[Dict[str, torch.Tensor]] = None, seed: int = 1234, init: str = "seeded",
+                 max_tokens: Optional[int] = None):
+        nat.require_device()
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.has_embed, self.has_head = has_embed, has_head
+        self.params = ShardParams(cfg, layer_ids, has_embed, has_head, self.device, with_grad=training)
+        if state_dict is not None:
+            self.params.load_hf_state_dict(state_dict)
+        elif init == "device":
+            self.params.init_on_device(seed)
+        else:
+            self.params.init_seeded(seed)
+        self.max_batch, self.max_seq = max_batch, max_seq
+        self.slots: List[CudaLayerGroup] = [CudaLayerGroup(cfg, self.params, max_batch, max_seq, max_tokens)
+                                            for _ in range(n_slots)]
+        dev = self.device
+        # decode-time fixed buffers (graph inputs/outputs), one set per slot
+        self.x_dec = [torch.zeros(max_batch, cfg.hidden, dtype=torch.bfloat16, device=dev) for _ in range(n_slots)]
+        self.ids_dec = [torch.zeros(max_batch, dtype=torch.int64, device=dev) for _ in range(n_slots)]
+        self.graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
+        if has_head:
+            self.head_ws = torch.empty(max(nat.lmhead_ws(min(max_batch, 8), cfg.vocab), max_batch * 64 * 8 + 256),
+                                       dtype=torch.uint8, device=dev)
+            self.logits_dec = torch.empty(max_batch, cfg.vocab, dtype=torch.bfloat16, device=dev)
+            self.hn = torch.empty(max_batch, cfg.hidden, dtype=torch.bfloat16, device=dev)
+
+    # ------------------------------------------------------------------------------------------ pieces
+    def embed(self, ids: torch.Tensor) -> torch.Tensor:
+        """[B,S] int64 -> [B,S,H]  (host-side ``embed_tokens`` in the reference, module.py:1023-1056)."""
+        return nat.embed_fwd(ids.contiguous(), self.params.v["embed"])
+
+    def prefill(self, hidden: torch.Tensor, past_len: int = 0, slot: int = 0) -> torch.Tensor:
+        return self.slots[slot].prefill(hidden, past_len)
+
+    def head_logits(self, hidden: torch.Tensor) -> torch.Tensor:
+        """final norm + lm_head over [N,H] -> bf16 logits [N,V]."""
+        cfg, v = self.cfg, self.params.v
+        n = hidden.shape[0]
+        if n <= 8:
+            return nat.gemv(hidden.contiguous(), v["head"], norm_w=v["norm"], eps=cfg.rms_eps)
+        hn = nat.rmsnorm_fwd(hidden.contiguous(), v["norm"], cfg.rms_eps)
+        return nat.gemm(hn, v["head"])
+
+    def head_argmax(self, hidden: torch.Tensor, ids_out: torch.Tensor):
+        """greedy next token for [B,H] rows -> ids_out [B] int64 (bit-exact target: torch.argmax of bf16 logits)."""
+        cfg, v = self.cfg, self.params.v
+        B = hidden.shape[0]
+        if B <= 8:
+            nat.lmhead_argmax(hidden, v["head"], v["norm"], cfg.rms_eps, ids_out, self.logits_dec[:B], self.head_ws)
+        else:
+            nat.rmsnorm_fwd(hidden, v["norm"], cfg.rms_eps, out=self.hn[:B])
+            nat.gemm(self.hn[:B], v["head"], out=self.logits_dec[:B])
+            nat.argmax_bf16(self.logits_dec[:B], ids_out, self.head_ws)
+
+    # ------------------------------------------------------------------------------------------ decode step
+    def _decode_body(self, slot: int, B: int):
+        x = self.x_dec[slot][:B]
+        if self.has_embed:
+            nat.embed_fwd(self.ids_dec[slot][:B], self.params.v["embed"], out=x)
+        self.slots[slot].decode_step_inplace(x)
+        if self.has_head:
+            self.head_argmax(x, self.ids_dec[slot][:B])
+
+    def decode(self, slot: int, B: int, use_graph: bool = True):
+        """One token for slot's rows: [embed ->] layers [-> norm + lm_head + argmax], as ONE graph launch.
+        Inputs/outputs are the fixed buffers ``ids_dec[slot]`` / ``x_dec[slot]``."""
+        if not use_graph:
+            self._decode_body(slot, B)
+            return
+        key = (slot, B)
+        g = self.graphs.get(key)
+        if g is None:
+            # warm up outside capture (first-use attribute setting, tensor-map cache), restoring the state it touches
+            grp = self.slots[slot]
+            saved = (grp.pos_dev.clone(), grp.kvlen_dev.clone(), self.ids_dec[slot].clone(), self.x_dec[slot].clone())
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._decode_body(slot, B)
+            torch.cuda.current_stream().wait_stream(side)
+            grp.pos_dev.copy_(saved[0]); grp.kvlen_dev.copy_(saved[1])
+            self.ids_dec[slot].copy_(saved[2]); self.x_dec[slot].copy_(saved[3])
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._decode_body(slot, B)
+            # capture does not execute; state is still the saved one
+            self.graphs[key] = g
+        g.replay()
+
+    def n_decode_launches(self, B: int) -> int:
+        """Kernel launches inside one decode step of this stage (for bench.py's gpu_launches claim)."""
+        per_layer = 9 if B <= 8 else 11   # gemv x4 (+norm fused) / rope / attn split+reduce / 2 advance amortised
+        n = len(self.slots[0].layer_ids) * (7 if B <= 8 else 9) + 2
+        if self.has_embed:
+            n += 1
+        if self.has_head:
+            n += 3 if B <= 8 else 4
+        return n

@@ -45,6 +45,7 @@ _SIGS = {
                                  c_int, c_int, c_int, c_void_p]),
     "tl_argmax_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "tl_advance_pos": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "tl_append_token": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
 }
 
 _lib: Optional[ctypes.CDLL] = None
@@ -243,3 +244,10 @@ def argmax_bf16(logits, ids_out, ws):
 def advance_pos(pos_dev, kv_len_dev, delta: int):
     require_device()
     _check(load().tl_advance_pos(_p(pos_dev), _p(kv_len_dev), delta, _stream()), "tl_advance_pos")
+
+
+def append_token(ids, out_tokens, step_dev):
+    require_device()
+    assert ids.dtype == torch.int64 and out_tokens.dtype == torch.int64 and out_tokens.is_contiguous()
+    B, ld = out_tokens.shape
+    _check(load().tl_append_token(_p(ids), _p(out_tokens), _p(step_dev), B, ld, _stream()), "tl_append_token")

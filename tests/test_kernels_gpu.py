@@ -4,9 +4,13 @@ Tolerances (stated once, used below):
   * ops with a single bf16 rounding point per output (norm, rope, Linear and its epilogues, embed):
     rel-L2 <= 1e-3 against the oracle's bf16 result (north_star tolerance; measured ~1e-4: only values
     whose fp32 accumulation order straddles a bf16 rounding boundary differ, by one ulp);
-  * attention: rel-L2 <= 2e-3 against 'sdpa_math' (the SDPA contract leaves the P rounding point
-    implementation-defined; torch's own CPU flash kernel differs from the same math by 2.7e-3,
-    tests/test_oracle_vs_hf.py) AND no less accurate than the oracle against fp32 attention;
+  * attention: the SDPA contract leaves the rounding point of P implementation-defined (flash kernels round
+    the un-normalised exp, the math path rounds the normalised probability; torch's own CPU flash kernel
+    differs from the same math by 2.7e-3 on unit-variance q/k, tests/test_oracle_vs_hf.py).  So:
+      (a) against exact fp32 attention on the same bf16 inputs the kernel must be no less accurate than
+          the oracle's bf16 result (<= 1.25x its error);
+      (b) rel-L2 <= 4e-3 against 'sdpa_math' on unit-variance q/k (peaked softmax, worst case);
+      (c) rel-L2 <= 1e-3 on the flat attention a random-init model actually produces (std 0.3 inputs);
   * token ids: exact.
 """
 import math
@@ -20,7 +24,7 @@ from tensorlink_b200.ml import configs as C
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3
-TOL_ATTN = 2e-3
+TOL_ATTN = 4e-3
 
 
 @pytest.fixture(scope="module")
@@ -205,8 +209,8 @@ def test_attn_prefill(nat, B, S, past, n_h, n_kv, d):
     lse = torch.empty(B, n_h, S, dtype=torch.float32, device="cuda")
     nat.attn_prefill_fwd(dev(q), dev(kc), dev(vc), out, lse, B, S, past, n_h, n_kv, d, d ** -0.5)
     got = out.cpu()
-    assert O.rel_l2(got, ref) <= TOL_ATTN
     assert O.rel_l2(got, f32) <= 1.25 * O.rel_l2(ref, f32) + 1e-4
+    assert O.rel_l2(got, ref) <= TOL_ATTN
     kk = O.repeat_kv(k, n_h // n_kv).float()
     s = (q.transpose(1, 2).float() @ kk.transpose(2, 3)) * d ** -0.5 + O.causal_mask(S, past + S, torch.float32)
     assert torch.allclose(lse.cpu(), torch.logsumexp(s, -1), rtol=1e-4, atol=1e-4)
@@ -226,8 +230,28 @@ def test_attn_decode(nat, B, kv_len, n_h, n_kv, d):
     kvl = torch.tensor([kv_len], dtype=torch.int32, device="cuda")
     nat.attn_decode_fwd(dev(q.reshape(B, n_h * d)), dev(kc), dev(vc), out, kvl, ws, B, n_h, n_kv, d, d ** -0.5)
     got = out.cpu().view(B, 1, -1)
-    assert O.rel_l2(got, ref) <= TOL_ATTN
     assert O.rel_l2(got, f32) <= 1.25 * O.rel_l2(ref, f32) + 1e-4
+    assert O.rel_l2(got, ref) <= TOL_ATTN
+
+
+@pytest.mark.parametrize("mode,B,S,past,n_h,n_kv,d", [("prefill", 2, 200, 0, 14, 2, 64), ("prefill", 1, 96, 160, 28, 4, 128),
+                                                      ("decode", 2, 1, 700, 28, 4, 128), ("decode", 1, 1, 255, 14, 2, 64)])
+def test_attn_flat_softmax_within_1e3(nat, mode, B, S, past, n_h, n_kv, d):
+    """Criterion (c): on low-variance scores (what a random-init model produces) both paths agree to 1e-3."""
+    q, k, v, ref, f32 = _attn_case(B, S, past, n_h, n_kv, d, seed=60, std=0.3)
+    T = past + S
+    kc = torch.zeros(B, n_kv, T + 5, d, dtype=torch.bfloat16)
+    vc = torch.zeros_like(kc)
+    kc[:, :, :T], vc[:, :, :T] = k, v
+    if mode == "prefill":
+        out = torch.empty(B, S, n_h * d, dtype=torch.bfloat16, device="cuda")
+        nat.attn_prefill_fwd(dev(q), dev(kc), dev(vc), out, None, B, S, past, n_h, n_kv, d, d ** -0.5)
+    else:
+        out = torch.empty(B, n_h * d, dtype=torch.bfloat16, device="cuda")
+        ws = torch.empty(nat.attn_decode_ws(B, n_h, d, T + 5), dtype=torch.uint8, device="cuda")
+        kvl = torch.tensor([T], dtype=torch.int32, device="cuda")
+        nat.attn_decode_fwd(dev(q.reshape(B, n_h * d)), dev(kc), dev(vc), out, kvl, ws, B, n_h, n_kv, d, d ** -0.5)
+    assert O.rel_l2(out.cpu().view(B, S, -1), ref) <= TOL
 
 
 @pytest.mark.parametrize("M,V,H", [(1, 1024, 256), (2, 151936, 896), (4, 2048, 512)])

@@ -1,0 +1,147 @@
+"""Model-level parity of the CUDA shard executor against the CPU oracle (same seeded weights and tokens).
+
+End-to-end tolerance: two bf16 pipelines with different (valid) rounding points diverge layer by layer; the
+reference's own spread — HF eager vs HF sdpa, both bit-pinned to the oracle's two attention modes — is the noise
+floor, so logits must satisfy rel-L2(gpu, oracle) <= 1.25 x rel-L2(oracle_eager, oracle_sdpa).  Per layer
+(teacher-forced on the oracle's input to that layer) the bound is 2e-3.  Token ids: exact wherever the oracle's
+top-2 logit margin exceeds MARGIN (random-init logits are nearly flat; a margin below the bf16 noise of the logits
+cannot be resolved by ANY bf16 implementation, including the reference on another CPU).
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import shard_oracle as O
+from tensorlink_b200.ml import configs as C
+from tensorlink_b200.ml.weights import init_state_dict, synthetic_tokens
+
+pytestmark = pytest.mark.gpu
+CASES = [C.TINY_QWEN2, C.TINY_QWEN2_D128, C.TINY_QWEN3]
+MARGIN = 0.05
+
+
+def make(cfg, **kw):
+    from tensorlink_b200.ml import DistributedModel
+    kw.setdefault("max_seq", 256)
+    return DistributedModel(cfg, training=False, **kw)
+
+
+@pytest.mark.parametrize("cfg", CASES, ids=lambda c: c.name)
+def test_forward_logits_vs_oracle(cfg):
+    sd = init_state_dict(cfg)
+    ids = synthetic_tokens(cfg, 2, 40)
+    with torch.no_grad():
+        ref = O.OracleModel(cfg, sd, "sdpa_math").logits(ids)
+        ref_e = O.OracleModel(cfg, sd, "eager").logits(ids)
+    got = make(cfg)(ids).logits.cpu()
+    floor = O.rel_l2(ref_e, ref)
+    err = O.rel_l2(got, ref)
+    print(f"{cfg.name}: rel_l2 gpu-vs-oracle {err:.3e}, reference eager-vs-sdpa floor {floor:.3e}")
+    assert err <= 1.25 * floor
+    safe = (lambda t: (t[..., 0] - t[..., 1]) > MARGIN)(ref.float().topk(2, -1).values)
+    assert torch.equal(got.float().argmax(-1)[safe], ref.float().argmax(-1)[safe])
+
+
+@pytest.mark.parametrize("cfg", CASES, ids=lambda c: c.name)
+def test_per_layer_teacher_forced(cfg):
+    from tensorlink_b200.ml.shard import CudaLayerGroup, ShardParams
+    sd = init_state_dict(cfg)
+    ids = synthetic_tokens(cfg, 2, 33)
+    m = O.OracleModel(cfg, sd, "sdpa_math")
+    per_layer = []
+    with torch.no_grad():
+        m.hidden(ids, per_layer=per_layer)
+        x0 = F.embedding(ids, m.embed)
+    inputs = [x0] + per_layer[:-1]
+    for li in range(cfg.n_layers):
+        p = ShardParams(cfg, [li], False, False, "cuda")
+        p.load_hf_state_dict(sd)
+        grp = CudaLayerGroup(cfg, p, 2, 64)
+        out = grp(hidden_states=inputs[li].cuda(), past_len=0)
+        assert set(out) == {"hidden_states", "past_len"}           # kwargs ∪ outputs (injector.py:252-260)
+        err = O.rel_l2(out["hidden_states"].cpu(), per_layer[li])
+        print(f"{cfg.name} layer {li}: rel_l2 {err:.3e}")
+        assert err <= 2e-3
+
+
+def _check_ids(got, ref, margins, prompt_len):
+    """exact up to the first step whose oracle margin is below MARGIN; a mismatch before that is a failure."""
+    new_got, new_ref = got[:, prompt_len:], ref[:, prompt_len:]
+    n_exact = 0
+    for b in range(ref.shape[0]):
+        for s in range(new_ref.shape[1]):
+            if margins[b, s] < MARGIN:
+                break                      # beyond an unresolvable step the sequences may legitimately fork
+            assert new_got[b, s] == new_ref[b, s], f"row {b} step {s}: margin {margins[b, s]:.3f}"
+            n_exact += 1
+    return n_exact
+
+
+@pytest.mark.parametrize("cfg", CASES, ids=lambda c: c.name)
+@pytest.mark.parametrize("B", [1, 2])
+def test_generate_greedy_ids(cfg, B):
+    sd = init_state_dict(cfg)
+    ids = synthetic_tokens(cfg, B, 12)
+    ref, margins = O.OracleModel(cfg, sd, "sdpa_math").generate(ids, 24, return_margins=True)
+    dm = make(cfg, max_batch=B)
+    got = dm.generate(ids, max_new_tokens=24).cpu()
+    got_nograph = dm.generate(ids, max_new_tokens=24, use_graph=False).cpu()
+    assert got.shape == ref.shape and torch.equal(got[:, :12], ids)
+    assert torch.equal(got, got_nograph)                      # CUDA-graph replay == eager launches, bit for bit
+    n = _check_ids(got, ref, margins, 12)
+    print(f"{cfg.name} B={B}: {n} of {B * 24} steps verified exact (margin >= {MARGIN}); "
+          f"full-sequence match: {torch.equal(got, ref)}")
+    assert n >= B * 4
+
+
+@pytest.mark.parametrize("cfg", [C.TINY_QWEN2_D128], ids=lambda c: c.name)
+def test_generate_teacher_forced_exact(cfg):
+    """Feed the ORACLE's generated sequence back as a prompt: every position's greedy choice must agree wherever the
+    oracle margin allows, independent of earlier forks."""
+    sd = init_state_dict(cfg)
+    ids = synthetic_tokens(cfg, 2, 8)
+    ref, margins = O.OracleModel(cfg, sd, "sdpa_math").generate(ids, 40, return_margins=True)
+    logits = make(cfg)(ref[:, :-1]).logits.cpu().float()
+    pred = logits.argmax(-1)[:, 7:]                            # predictions for the 40 generated positions
+    safe = margins >= MARGIN
+    assert safe.float().mean() > 0.3
+    assert torch.equal(pred[safe], ref[:, 8:][safe])
+
+
+def test_batched_decode_gemm_path():
+    """B = 16 rows decode through the tcgen05 GEMM path; rows are independent, so row i must equal a B=1 run."""
+    cfg = C.TINY_QWEN2_D128
+    ids = synthetic_tokens(cfg, 16, 10)
+    big = make(cfg, max_batch=16).generate(ids, max_new_tokens=12).cpu()
+    sd = init_state_dict(cfg)
+    ref, margins = O.OracleModel(cfg, sd, "sdpa_math").generate(ids, 12, return_margins=True)
+    assert _check_ids(big, ref, margins, 10) >= 32
+
+
+def test_micro_batched_generate_equals_single():
+    cfg = C.TINY_QWEN2
+    ids = synthetic_tokens(cfg, 4, 9)
+    a = make(cfg, max_batch=4).generate(ids, max_new_tokens=10).cpu()
+    b = make(cfg, max_batch=4, n_pipelines=2).generate(ids, max_new_tokens=10).cpu()
+    sd = init_state_dict(cfg)
+    ref, margins = O.OracleModel(cfg, sd, "sdpa_math").generate(ids, 10, return_margins=True)
+    assert _check_ids(a, ref, margins, 9) >= 8 and _check_ids(b, ref, margins, 9) >= 8
+
+
+def test_full_size_qwen25_05b_properties():
+    """BASELINE config 2 at full size (the oracle would take minutes): size-independent properties.
+    (1) graph replay == eager launches; (2) incremental decode == one-shot prefill (KV-cache consistency):
+    the ids produced step by step must be the argmax of a single forward over the final sequence wherever the
+    one-shot top-2 margin is resolvable; (3) generation is deterministic run to run."""
+    cfg = C.QWEN25_05B
+    dm = make(cfg, max_batch=1, max_seq=128, init="device")
+    ids = synthetic_tokens(cfg, 1, 32)
+    a = dm.generate(ids, max_new_tokens=24).cpu()
+    b = dm.generate(ids, max_new_tokens=24, use_graph=False).cpu()
+    c = dm.generate(ids, max_new_tokens=24).cpu()
+    assert torch.equal(a, b) and torch.equal(a, c)
+    logits = dm(a[:, :-1]).logits.cpu().float()
+    top2 = logits.topk(2, -1).values
+    safe = ((top2[..., 0] - top2[..., 1]) > MARGIN)[:, 31:]
+    assert torch.equal(logits.argmax(-1)[:, 31:][safe], a[:, 32:][safe])
+    assert safe.float().mean() > 0.2
