@@ -81,6 +81,18 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference leg
+def usable_cores():
+    """Cores this process may actually run on (affinity mask and cgroup quota), not the box's logical CPU count."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(int(q) / int(per))))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
 class CpuReference:
     """The reference's CPU shard math (oracle port of the HF decoder layers the reference executes) on a bounded
     sample: ``budget_layers`` of the model's layers at full width + the full-vocabulary lm_head, ``prompt``-token
@@ -91,7 +103,7 @@ class CpuReference:
         from oracle import shard_oracle as O
         from tensorlink_b200.ml.weights import init_state_dict, synthetic_tokens
         self.O, self.torch = O, torch
-        self.threads = threads or os.cpu_count()
+        self.threads = threads or usable_cores()
         torch.set_num_threads(self.threads)
         self.cfg, self.rows, self.prompt, self.L = cfg, rows, prompt, budget_layers
         self.sub = cfg.scaled(n_layers=budget_layers)

@@ -4,6 +4,8 @@
 // an item and split K between them with a CTA-coalesced stride; 8/WPI items are in flight per CTA.
 // Every lane keeps 2*G independent 16-byte loads in flight per k-iteration (ld.global.nc, L1 no-allocate).
 // Algorithmic bytes per launch = 2*N*K (weights) + O(M*(K+N)) activations.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace tl {
@@ -214,6 +216,18 @@ static int dispatch_g(int g, int wpi, const void* x, const void* W, void* y, int
     }
 }
 
+int gemv_stream_dispatch(const void* x, const void* W, void* y, int M, int N, int K, const void* bias,
+                         const void* residual, const void* norm_w, float eps, int flags, cudaStream_t st);
+
+static bool use_stream_kernel() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("TL_GEMV_IMPL");
+        v = (e && e[0] == 'r') ? 0 : 1;     // TL_GEMV_IMPL=reg forces the register-streaming kernel (A/B tests)
+    }
+    return v == 1;
+}
+
 }  // namespace tl
 
 extern "C" int tl_gemv_bf16(const void* x, const void* W, void* y, int M, int N, int K, const void* bias,
@@ -244,6 +258,10 @@ extern "C" int tl_gemv_bf16(const void* x, const void* W, void* y, int M, int N,
     // indexes only m < M... (rows beyond M would read x out of bounds), so dispatch exactly for 1..4 and
     // split larger M into two calls.
     auto run = [&](int m, const bf16* xx, bf16* yy, const bf16* rr) -> int {
+        if (use_stream_kernel()) {
+            const int rc = gemv_stream_dispatch(xx, W, yy, m, N, K, bias, rr, norm_w, eps, flags, st);
+            if (rc != 1) return rc;
+        }
         switch (m) {
             case 1: return dispatch_g<1>(g, wpi, xx, W, yy, N, K, bias, rr, norm_w, eps, flags, st);
             case 2: return dispatch_g<2>(g, wpi, xx, W, yy, N, K, bias, rr, norm_w, eps, flags, st);

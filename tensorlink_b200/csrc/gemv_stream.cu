@@ -1,0 +1,241 @@
+// Decode-shaped Linear, v2: persistent weight-streaming GEMV with a bulk-copy (TMA) producer warp.
+//
+// One CTA per SM.  Each CTA owns a contiguous range of row PAIRS of W (pair = gate/up for the SwiGLU epilogue)
+// sized so every SM streams the same number of bytes (+-1 pair).  Warp 8 is the producer: it walks the CTA's
+// rows in groups of 8 pairs x KC-column chunks and issues one cp.async.bulk per row chunk into a deep shared
+// memory ring (mbarrier full/empty, up to ~190 KB in flight per SM), never waiting on the math.  Warps 0..7 are
+// consumers: warp w owns pair w of the current group for all its K chunks, so the dot products finish with one
+// warp reduction and no cross-warp traffic; x (optionally RMS-normalised, HF rounding) is staged once per CTA
+// while the producer is already streaming.  Algorithmic bytes per launch = 2*N*K.
+#include "common.cuh"
+
+namespace tl {
+
+constexpr int GS_CONSUMER_WARPS = 8;
+constexpr int GS_THREADS = (GS_CONSUMER_WARPS + 1) * 32;
+constexpr int GS_ROWS = 2 * GS_CONSUMER_WARPS;   // rows per stage
+constexpr int GS_MAX_STAGES = 16;
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int M>
+__global__ void __launch_bounds__(GS_THREADS, 1)
+gemv_stream_kernel(const bf16* __restrict__ x, const bf16* __restrict__ W, bf16* __restrict__ y, int N, int K,
+                   const bf16* __restrict__ bias, const bf16* __restrict__ residual, const bf16* __restrict__ norm_w,
+                   float eps, int flags, int KC, int n_stages) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int stage_bytes = GS_ROWS * KC * 2;
+    unsigned char* ring = smem;                                                 // [n_stages][GS_ROWS][KC] bf16
+    bf16* xs = reinterpret_cast<bf16*>(smem + (size_t)n_stages * stage_bytes);  // [M][K]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)n_stages * stage_bytes + (((size_t)M * K * 2 + 15) & ~(size_t)15));
+    uint64_t* empty_bar = full_bar + GS_MAX_STAGES;
+    __shared__ float s_part[GS_CONSUMER_WARPS][M];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int npairs = N >> 1;
+    const int p_begin = (int)((long long)blockIdx.x * npairs / gridDim.x);
+    const int p_end = (int)((long long)(blockIdx.x + 1) * npairs / gridDim.x);
+    const int n_groups = (p_end - p_begin + GS_CONSUMER_WARPS - 1) / GS_CONSUMER_WARPS;
+    const int n_chunks = (K + KC - 1) / KC;
+
+    if (tid == 0) {
+        for (int s = 0; s < n_stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], GS_CONSUMER_WARPS);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp == GS_CONSUMER_WARPS) {
+        // ================================================================= producer
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int g = 0; g < n_groups; ++g) {
+            const int pair0 = p_begin + g * GS_CONSUMER_WARPS;
+            const int rows_valid = min(GS_ROWS, 2 * (p_end - pair0));
+            for (int c = 0; c < n_chunks; ++c) {
+                const int k0 = c * KC;
+                const uint32_t bytes = (uint32_t)min(KC, K - k0) * 2u;
+                if (lane == 0) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], bytes * (uint32_t)rows_valid);
+                }
+                __syncwarp();
+                if (lane < rows_valid)
+                    bulk_load_1d(ring + (size_t)stage * stage_bytes + (size_t)lane * KC * 2,
+                                 W + ((size_t)(2 * pair0 + lane)) * K + k0, bytes, &full_bar[stage]);
+                if (++stage == n_stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ================================================================= consumers
+        const int ctid = tid;   // 0..255
+        const int nvec = K >> 3;
+        if (norm_w) {
+            float ss[M];
+#pragma unroll
+            for (int m = 0; m < M; ++m) ss[m] = 0.f;
+            for (int v = ctid; v < nvec; v += GS_CONSUMER_WARPS * 32) {
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    const uint4 u = reinterpret_cast<const uint4*>(x + (size_t)m * K)[v];
+                    const uint32_t* u32 = reinterpret_cast<const uint32_t*>(&u);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float a = bf16_lo(u32[j]), b = bf16_hi(u32[j]);
+                        ss[m] += a * a + b * b;
+                    }
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                const float t = warp_sum(ss[m]);
+                if (lane == 0) s_part[warp][m] = t;
+            }
+            named_bar_sync(1, GS_CONSUMER_WARPS * 32);
+            float rstd[M];
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                float t = 0.f;
+#pragma unroll
+                for (int w = 0; w < GS_CONSUMER_WARPS; ++w) t += s_part[w][m];
+                rstd[m] = 1.0f / sqrtf(t / (float)K + eps);
+            }
+            for (int v = ctid; v < nvec; v += GS_CONSUMER_WARPS * 32) {
+                const uint4 g = reinterpret_cast<const uint4*>(norm_w)[v];
+                const uint32_t* g32 = reinterpret_cast<const uint32_t*>(&g);
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    const uint4 u = reinterpret_cast<const uint4*>(x + (size_t)m * K)[v];
+                    uint4 o;
+                    const uint32_t* u32 = reinterpret_cast<const uint32_t*>(&u);
+                    uint32_t* o32 = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        o32[j] = pack_bf16(bf16_lo(g32[j]) * rbf(bf16_lo(u32[j]) * rstd[m]),
+                                           bf16_hi(g32[j]) * rbf(bf16_hi(u32[j]) * rstd[m]));
+                    reinterpret_cast<uint4*>(xs + (size_t)m * K)[v] = o;
+                }
+            }
+        } else {
+            for (int v = ctid; v < nvec * M; v += GS_CONSUMER_WARPS * 32)
+                reinterpret_cast<uint4*>(xs)[v] = reinterpret_cast<const uint4*>(x)[v];
+        }
+        named_bar_sync(1, GS_CONSUMER_WARPS * 32);
+
+        const bool swiglu = flags & TL_EPI_SWIGLU;
+        const int n_out = swiglu ? npairs : N;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int g = 0; g < n_groups; ++g) {
+            const int pair = p_begin + g * GS_CONSUMER_WARPS + warp;
+            const bool valid = pair < p_end;
+            float acc[2][M];
+#pragma unroll
+            for (int m = 0; m < M; ++m) acc[0][m] = acc[1][m] = 0.f;
+            for (int c = 0; c < n_chunks; ++c) {
+                const int k0 = c * KC;
+                const int vecs = min(KC, K - k0) >> 3;
+                mbar_wait(&full_bar[stage], phase);
+                if (valid) {
+                    const uint4* r0 = reinterpret_cast<const uint4*>(ring + (size_t)stage * stage_bytes + (size_t)(2 * warp) * KC * 2);
+                    const uint4* r1 = reinterpret_cast<const uint4*>(ring + (size_t)stage * stage_bytes + (size_t)(2 * warp + 1) * KC * 2);
+#pragma unroll 4
+                    for (int v = lane; v < vecs; v += 32) {
+                        const uint4 w0 = r0[v], w1 = r1[v];
+                        const uint32_t* a32 = reinterpret_cast<const uint32_t*>(&w0);
+                        const uint32_t* b32 = reinterpret_cast<const uint32_t*>(&w1);
+#pragma unroll
+                        for (int m = 0; m < M; ++m) {
+                            const uint4 xv = reinterpret_cast<const uint4*>(xs + (size_t)m * K + k0)[v];
+                            const uint32_t* x32 = reinterpret_cast<const uint32_t*>(&xv);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float xl = bf16_lo(x32[j]), xh = bf16_hi(x32[j]);
+                                acc[0][m] = fmaf(bf16_lo(a32[j]), xl, acc[0][m]);
+                                acc[0][m] = fmaf(bf16_hi(a32[j]), xh, acc[0][m]);
+                                acc[1][m] = fmaf(bf16_lo(b32[j]), xl, acc[1][m]);
+                                acc[1][m] = fmaf(bf16_hi(b32[j]), xh, acc[1][m]);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[stage]);
+                if (++stage == n_stages) { stage = 0; phase ^= 1; }
+            }
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                acc[0][m] = warp_sum(acc[0][m]);
+                acc[1][m] = warp_sum(acc[1][m]);
+            }
+            if (valid && lane == 0) {
+                const int r0 = 2 * pair;
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    float v0 = acc[0][m], v1 = acc[1][m];
+                    if (flags & TL_EPI_BIAS) {
+                        v0 += bf2f(bias[r0]);
+                        v1 += bf2f(bias[r0 + 1]);
+                    }
+                    if (swiglu) {
+                        const float gate = rbf(v0), up = rbf(v1);
+                        y[(size_t)m * n_out + pair] = f2bf(rbf(silu_f(gate)) * up);
+                    } else {
+                        float t0 = rbf(v0), t1 = rbf(v1);
+                        if (flags & TL_EPI_RESIDUAL) {
+                            t0 += bf2f(residual[(size_t)m * N + r0]);
+                            t1 += bf2f(residual[(size_t)m * N + r0 + 1]);
+                        }
+                        *reinterpret_cast<uint32_t*>(y + (size_t)m * N + r0) = pack_bf16(t0, t1);
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int M>
+static int launch_stream(const void* x, const void* W, void* y, int N, int K, const void* bias, const void* residual,
+                         const void* norm_w, float eps, int flags, cudaStream_t st) {
+    auto kern = gemv_stream_kernel<M>;
+    constexpr int SMEM_CAP = 220 * 1024;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAP) != cudaSuccess)
+            return check_launch("tl_gemv_bf16/stream (smem attr)");
+        attr_done = true;
+    }
+    const int KC = K >= 2048 ? 1024 : 512;
+    const int stage_bytes = GS_ROWS * KC * 2;
+    const size_t xs_bytes = (((size_t)M * K * 2) + 15) & ~(size_t)15;
+    const size_t fixed = xs_bytes + 2 * GS_MAX_STAGES * sizeof(uint64_t);
+    int n_stages = (int)((SMEM_CAP - fixed) / stage_bytes);
+    if (n_stages > GS_MAX_STAGES) n_stages = GS_MAX_STAGES;
+    if (n_stages < 2) return 1;   // caller falls back to the register-streaming kernel
+    const size_t smem = (size_t)n_stages * stage_bytes + fixed;
+    const int npairs = N >> 1;
+    int grid = sm_count();
+    if (grid > npairs) grid = npairs;
+    kern<<<grid, GS_THREADS, smem, st>>>((const bf16*)x, (const bf16*)W, (bf16*)y, N, K, (const bf16*)bias,
+                                         (const bf16*)residual, (const bf16*)norm_w, eps, flags, KC, n_stages);
+    return check_launch("tl_gemv_bf16/stream");
+}
+
+// returns TL_OK, an error, or 1 = "not applicable, use the fallback kernel"
+int gemv_stream_dispatch(const void* x, const void* W, void* y, int M, int N, int K, const void* bias,
+                         const void* residual, const void* norm_w, float eps, int flags, cudaStream_t st) {
+    if (K % 8 != 0 || ((uintptr_t)W & 15)) return 1;
+    switch (M) {
+        case 1: return launch_stream<1>(x, W, y, N, K, bias, residual, norm_w, eps, flags, st);
+        case 2: return launch_stream<2>(x, W, y, N, K, bias, residual, norm_w, eps, flags, st);
+        case 3: return launch_stream<3>(x, W, y, N, K, bias, residual, norm_w, eps, flags, st);
+        case 4: return launch_stream<4>(x, W, y, N, K, bias, residual, norm_w, eps, flags, st);
+        default: return 1;
+    }
+}
+
+}  // namespace tl
