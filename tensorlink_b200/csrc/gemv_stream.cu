@@ -2,19 +2,22 @@
 //
 // One CTA per SM.  Each CTA owns a contiguous range of row PAIRS of W (pair = gate/up for the SwiGLU epilogue)
 // sized so every SM streams the same number of bytes (+-1 pair).  Warp 8 is the producer: it walks the CTA's
-// rows in groups of 8 pairs x KC-column chunks and issues one cp.async.bulk per row chunk into a deep shared
-// memory ring (mbarrier full/empty, up to ~190 KB in flight per SM), never waiting on the math.  Warps 0..7 are
-// consumers: warp w owns pair w of the current group for all its K chunks, so the dot products finish with one
-// warp reduction and no cross-warp traffic; x (optionally RMS-normalised, HF rounding) is staged once per CTA
-// while the producer is already streaming.  Algorithmic bytes per launch = 2*N*K.
+// rows and issues cp.async.bulk copies of <= 16 KB "stages" into a deep shared-memory ring (mbarrier full/empty,
+// ~190 KB in flight per SM), never waiting on the math.  A stage is either P whole consecutive pairs (K small:
+// rows are contiguous in memory, ONE copy) or one K-chunk of one pair (K large: two row-segment copies).  Stages
+// are issued round-robin over the 8 consumer warps; warp w owns every 8th unit for all of its K chunks, so a dot
+// product finishes with one warp reduction and no cross-warp traffic.  x (optionally RMS-normalised with HF
+// rounding) is staged once per CTA while the producer is already streaming.
+// Algorithmic bytes per launch = 2*N*K.
 #include "common.cuh"
 
 namespace tl {
 
 constexpr int GS_CONSUMER_WARPS = 8;
 constexpr int GS_THREADS = (GS_CONSUMER_WARPS + 1) * 32;
-constexpr int GS_ROWS = 2 * GS_CONSUMER_WARPS;   // rows per stage
 constexpr int GS_MAX_STAGES = 16;
+constexpr int GS_STAGE_BYTES = 16 * 1024;
+constexpr int GS_KC = 4096;            // K chunk (elements) when a pair does not fit one stage
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -24,12 +27,11 @@ template <int M>
 __global__ void __launch_bounds__(GS_THREADS, 1)
 gemv_stream_kernel(const bf16* __restrict__ x, const bf16* __restrict__ W, bf16* __restrict__ y, int N, int K,
                    const bf16* __restrict__ bias, const bf16* __restrict__ residual, const bf16* __restrict__ norm_w,
-                   float eps, int flags, int KC, int n_stages) {
+                   float eps, int flags, int P, int n_stages) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int stage_bytes = GS_ROWS * KC * 2;
-    unsigned char* ring = smem;                                                 // [n_stages][GS_ROWS][KC] bf16
-    bf16* xs = reinterpret_cast<bf16*>(smem + (size_t)n_stages * stage_bytes);  // [M][K]
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)n_stages * stage_bytes + (((size_t)M * K * 2 + 15) & ~(size_t)15));
+    unsigned char* ring = smem;                                                    // [n_stages][GS_STAGE_BYTES]
+    bf16* xs = reinterpret_cast<bf16*>(smem + (size_t)n_stages * GS_STAGE_BYTES);  // [M][K]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)n_stages * GS_STAGE_BYTES + (((size_t)M * K * 2 + 15) & ~(size_t)15));
     uint64_t* empty_bar = full_bar + GS_MAX_STAGES;
     __shared__ float s_part[GS_CONSUMER_WARPS][M];
 
@@ -37,48 +39,62 @@ gemv_stream_kernel(const bf16* __restrict__ x, const bf16* __restrict__ W, bf16*
     const int npairs = N >> 1;
     const int p_begin = (int)((long long)blockIdx.x * npairs / gridDim.x);
     const int p_end = (int)((long long)(blockIdx.x + 1) * npairs / gridDim.x);
-    const int n_groups = (p_end - p_begin + GS_CONSUMER_WARPS - 1) / GS_CONSUMER_WARPS;
+    const int n_units = (p_end - p_begin + P - 1) / P;                 // unit = P consecutive pairs
+    const int n_groups = (n_units + GS_CONSUMER_WARPS - 1) / GS_CONSUMER_WARPS;
+    const bool chunked = K > GS_KC || (size_t)K * 4 > GS_STAGE_BYTES;  // a pair does not fit one stage
+    const int KC = chunked ? GS_KC : K;
     const int n_chunks = (K + KC - 1) / KC;
 
     if (tid == 0) {
         for (int s = 0; s < n_stages; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], GS_CONSUMER_WARPS);
+            mbar_init(&empty_bar[s], 1);
         }
         fence_barrier_init();
     }
     __syncthreads();
 
     if (warp == GS_CONSUMER_WARPS) {
-        // ================================================================= producer
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int g = 0; g < n_groups; ++g) {
-            const int pair0 = p_begin + g * GS_CONSUMER_WARPS;
-            const int rows_valid = min(GS_ROWS, 2 * (p_end - pair0));
-            for (int c = 0; c < n_chunks; ++c) {
-                const int k0 = c * KC;
-                const uint32_t bytes = (uint32_t)min(KC, K - k0) * 2u;
-                if (lane == 0) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_expect_tx(&full_bar[stage], bytes * (uint32_t)rows_valid);
+        // ================================================================= producer (one elected lane)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int g = 0; g < n_groups; ++g) {
+                for (int c = 0; c < n_chunks; ++c) {
+                    for (int w = 0; w < GS_CONSUMER_WARPS; ++w) {
+                        const int unit = g * GS_CONSUMER_WARPS + w;
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        unsigned char* dst = ring + (size_t)stage * GS_STAGE_BYTES;
+                        if (unit >= n_units) {
+                            mbar_expect_tx(&full_bar[stage], 0);
+                        } else {
+                            const int pair0 = p_begin + unit * P;
+                            const int np = min(P, p_end - pair0);
+                            if (!chunked) {      // np pairs = 2*np whole rows, contiguous in memory: one copy
+                                const uint32_t bytes = (uint32_t)(2 * np) * (uint32_t)K * 2u;
+                                mbar_expect_tx(&full_bar[stage], bytes);
+                                bulk_load_1d(dst, W + (size_t)(2 * pair0) * K, bytes, &full_bar[stage]);
+                            } else {             // one K chunk of the two rows of one pair: two copies
+                                const int k0 = c * KC;
+                                const uint32_t bytes = (uint32_t)min(KC, K - k0) * 2u;
+                                mbar_expect_tx(&full_bar[stage], 2 * bytes);
+                                bulk_load_1d(dst, W + (size_t)(2 * pair0) * K + k0, bytes, &full_bar[stage]);
+                                bulk_load_1d(dst + (size_t)KC * 2, W + (size_t)(2 * pair0 + 1) * K + k0, bytes, &full_bar[stage]);
+                            }
+                        }
+                        if (++stage == n_stages) { stage = 0; phase ^= 1; }
+                    }
                 }
-                __syncwarp();
-                if (lane < rows_valid)
-                    bulk_load_1d(ring + (size_t)stage * stage_bytes + (size_t)lane * KC * 2,
-                                 W + ((size_t)(2 * pair0 + lane)) * K + k0, bytes, &full_bar[stage]);
-                if (++stage == n_stages) { stage = 0; phase ^= 1; }
             }
         }
     } else {
         // ================================================================= consumers
-        const int ctid = tid;   // 0..255
         const int nvec = K >> 3;
         if (norm_w) {
             float ss[M];
 #pragma unroll
             for (int m = 0; m < M; ++m) ss[m] = 0.f;
-            for (int v = ctid; v < nvec; v += GS_CONSUMER_WARPS * 32) {
+            for (int v = tid; v < nvec; v += GS_CONSUMER_WARPS * 32) {
 #pragma unroll
                 for (int m = 0; m < M; ++m) {
                     const uint4 u = reinterpret_cast<const uint4*>(x + (size_t)m * K)[v];
@@ -104,7 +120,7 @@ gemv_stream_kernel(const bf16* __restrict__ x, const bf16* __restrict__ W, bf16*
                 for (int w = 0; w < GS_CONSUMER_WARPS; ++w) t += s_part[w][m];
                 rstd[m] = 1.0f / sqrtf(t / (float)K + eps);
             }
-            for (int v = ctid; v < nvec; v += GS_CONSUMER_WARPS * 32) {
+            for (int v = tid; v < nvec; v += GS_CONSUMER_WARPS * 32) {
                 const uint4 g = reinterpret_cast<const uint4*>(norm_w)[v];
                 const uint32_t* g32 = reinterpret_cast<const uint32_t*>(&g);
 #pragma unroll
@@ -121,78 +137,99 @@ gemv_stream_kernel(const bf16* __restrict__ x, const bf16* __restrict__ W, bf16*
                 }
             }
         } else {
-            for (int v = ctid; v < nvec * M; v += GS_CONSUMER_WARPS * 32)
+            for (int v = tid; v < nvec * M; v += GS_CONSUMER_WARPS * 32)
                 reinterpret_cast<uint4*>(xs)[v] = reinterpret_cast<const uint4*>(x)[v];
         }
         named_bar_sync(1, GS_CONSUMER_WARPS * 32);
 
         const bool swiglu = flags & TL_EPI_SWIGLU;
         const int n_out = swiglu ? npairs : N;
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int g = 0; g < n_groups; ++g) {
-            const int pair = p_begin + g * GS_CONSUMER_WARPS + warp;
-            const bool valid = pair < p_end;
-            float acc[2][M];
+        // epilogue for one finished pair (all lanes hold the reduced sums)
+        auto finish = [&](int pair, const float (&a0)[M], const float (&a1)[M]) {
+            if (lane != 0) return;
+            const int r0 = 2 * pair;
 #pragma unroll
-            for (int m = 0; m < M; ++m) acc[0][m] = acc[1][m] = 0.f;
-            for (int c = 0; c < n_chunks; ++c) {
-                const int k0 = c * KC;
-                const int vecs = min(KC, K - k0) >> 3;
-                mbar_wait(&full_bar[stage], phase);
-                if (valid) {
-                    const uint4* r0 = reinterpret_cast<const uint4*>(ring + (size_t)stage * stage_bytes + (size_t)(2 * warp) * KC * 2);
-                    const uint4* r1 = reinterpret_cast<const uint4*>(ring + (size_t)stage * stage_bytes + (size_t)(2 * warp + 1) * KC * 2);
+            for (int m = 0; m < M; ++m) {
+                float v0 = a0[m], v1 = a1[m];
+                if (flags & TL_EPI_BIAS) {
+                    v0 += bf2f(bias[r0]);
+                    v1 += bf2f(bias[r0 + 1]);
+                }
+                if (swiglu) {
+                    const float gate = rbf(v0), up = rbf(v1);
+                    y[(size_t)m * n_out + pair] = f2bf(rbf(silu_f(gate)) * up);
+                } else {
+                    float t0 = rbf(v0), t1 = rbf(v1);
+                    if (flags & TL_EPI_RESIDUAL) {
+                        t0 += bf2f(residual[(size_t)m * N + r0]);
+                        t1 += bf2f(residual[(size_t)m * N + r0 + 1]);
+                    }
+                    *reinterpret_cast<uint32_t*>(y + (size_t)m * N + r0) = pack_bf16(t0, t1);
+                }
+            }
+        };
+        // dot product of `vecs` 16-byte vectors of two rows against x[k0..]
+        auto dot2 = [&](const uint4* r0, const uint4* r1, int k0, int vecs, float (&a0)[M], float (&a1)[M]) {
 #pragma unroll 4
-                    for (int v = lane; v < vecs; v += 32) {
-                        const uint4 w0 = r0[v], w1 = r1[v];
-                        const uint32_t* a32 = reinterpret_cast<const uint32_t*>(&w0);
-                        const uint32_t* b32 = reinterpret_cast<const uint32_t*>(&w1);
+            for (int v = lane; v < vecs; v += 32) {
+                const uint4 w0 = r0[v], w1 = r1[v];
+                const uint32_t* a32 = reinterpret_cast<const uint32_t*>(&w0);
+                const uint32_t* b32 = reinterpret_cast<const uint32_t*>(&w1);
 #pragma unroll
-                        for (int m = 0; m < M; ++m) {
-                            const uint4 xv = reinterpret_cast<const uint4*>(xs + (size_t)m * K + k0)[v];
-                            const uint32_t* x32 = reinterpret_cast<const uint32_t*>(&xv);
+                for (int m = 0; m < M; ++m) {
+                    const uint4 xv = reinterpret_cast<const uint4*>(xs + (size_t)m * K + k0)[v];
+                    const uint32_t* x32 = reinterpret_cast<const uint32_t*>(&xv);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float xl = bf16_lo(x32[j]), xh = bf16_hi(x32[j]);
-                                acc[0][m] = fmaf(bf16_lo(a32[j]), xl, acc[0][m]);
-                                acc[0][m] = fmaf(bf16_hi(a32[j]), xh, acc[0][m]);
-                                acc[1][m] = fmaf(bf16_lo(b32[j]), xl, acc[1][m]);
-                                acc[1][m] = fmaf(bf16_hi(b32[j]), xh, acc[1][m]);
-                            }
+                    for (int j = 0; j < 4; ++j) {
+                        const float xl = bf16_lo(x32[j]), xh = bf16_hi(x32[j]);
+                        a0[m] = fmaf(bf16_lo(a32[j]), xl, a0[m]);
+                        a0[m] = fmaf(bf16_hi(a32[j]), xh, a0[m]);
+                        a1[m] = fmaf(bf16_lo(b32[j]), xl, a1[m]);
+                        a1[m] = fmaf(bf16_hi(b32[j]), xh, a1[m]);
+                    }
+                }
+            }
+        };
+        // this warp's stages are sequence numbers warp, warp+8, warp+16, ... of the producer's order
+        int seq = warp;
+        for (int g = 0; g < n_groups; ++g) {
+            const int unit = g * GS_CONSUMER_WARPS + warp;
+            const bool valid = unit < n_units;
+            const int pair0 = p_begin + unit * P;
+            float a0[M], a1[M];
+#pragma unroll
+            for (int m = 0; m < M; ++m) a0[m] = a1[m] = 0.f;
+            for (int c = 0; c < n_chunks; ++c, seq += GS_CONSUMER_WARPS) {
+                const int stage = seq % n_stages;
+                const uint32_t phase = (uint32_t)(seq / n_stages) & 1u;
+                mbar_wait(&full_bar[stage], phase);
+                const unsigned char* src = ring + (size_t)stage * GS_STAGE_BYTES;
+                if (valid) {
+                    if (!chunked) {
+                        const int np = min(P, p_end - pair0);
+                        for (int pp = 0; pp < np; ++pp) {
+                            float b0[M], b1[M];
+#pragma unroll
+                            for (int m = 0; m < M; ++m) b0[m] = b1[m] = 0.f;
+                            dot2(reinterpret_cast<const uint4*>(src + (size_t)(2 * pp) * K * 2),
+                                 reinterpret_cast<const uint4*>(src + (size_t)(2 * pp + 1) * K * 2), 0, nvec, b0, b1);
+#pragma unroll
+                            for (int m = 0; m < M; ++m) { b0[m] = warp_sum(b0[m]); b1[m] = warp_sum(b1[m]); }
+                            finish(pair0 + pp, b0, b1);
                         }
+                    } else {
+                        const int k0 = c * KC;
+                        dot2(reinterpret_cast<const uint4*>(src), reinterpret_cast<const uint4*>(src + (size_t)KC * 2), k0,
+                             min(KC, K - k0) >> 3, a0, a1);
                     }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty_bar[stage]);
-                if (++stage == n_stages) { stage = 0; phase ^= 1; }
             }
+            if (valid && chunked) {
 #pragma unroll
-            for (int m = 0; m < M; ++m) {
-                acc[0][m] = warp_sum(acc[0][m]);
-                acc[1][m] = warp_sum(acc[1][m]);
-            }
-            if (valid && lane == 0) {
-                const int r0 = 2 * pair;
-#pragma unroll
-                for (int m = 0; m < M; ++m) {
-                    float v0 = acc[0][m], v1 = acc[1][m];
-                    if (flags & TL_EPI_BIAS) {
-                        v0 += bf2f(bias[r0]);
-                        v1 += bf2f(bias[r0 + 1]);
-                    }
-                    if (swiglu) {
-                        const float gate = rbf(v0), up = rbf(v1);
-                        y[(size_t)m * n_out + pair] = f2bf(rbf(silu_f(gate)) * up);
-                    } else {
-                        float t0 = rbf(v0), t1 = rbf(v1);
-                        if (flags & TL_EPI_RESIDUAL) {
-                            t0 += bf2f(residual[(size_t)m * N + r0]);
-                            t1 += bf2f(residual[(size_t)m * N + r0 + 1]);
-                        }
-                        *reinterpret_cast<uint32_t*>(y + (size_t)m * N + r0) = pack_bf16(t0, t1);
-                    }
-                }
+                for (int m = 0; m < M; ++m) { a0[m] = warp_sum(a0[m]); a1[m] = warp_sum(a1[m]); }
+                finish(pair0, a0, a1);
             }
         }
     }
@@ -209,19 +246,21 @@ static int launch_stream(const void* x, const void* W, void* y, int N, int K, co
             return check_launch("tl_gemv_bf16/stream (smem attr)");
         attr_done = true;
     }
-    const int KC = K >= 2048 ? 1024 : 512;
-    const int stage_bytes = GS_ROWS * KC * 2;
     const size_t xs_bytes = (((size_t)M * K * 2) + 15) & ~(size_t)15;
     const size_t fixed = xs_bytes + 2 * GS_MAX_STAGES * sizeof(uint64_t);
-    int n_stages = (int)((SMEM_CAP - fixed) / stage_bytes);
+    int n_stages = (int)((SMEM_CAP - fixed) / GS_STAGE_BYTES);
     if (n_stages > GS_MAX_STAGES) n_stages = GS_MAX_STAGES;
-    if (n_stages < 2) return 1;   // caller falls back to the register-streaming kernel
-    const size_t smem = (size_t)n_stages * stage_bytes + fixed;
+    if (n_stages < 3) return 1;   // caller falls back to the register-streaming kernel
+    const size_t smem = (size_t)n_stages * GS_STAGE_BYTES + fixed;
+    const bool chunked = K > GS_KC || (size_t)K * 4 > GS_STAGE_BYTES;
+    int P = chunked ? 1 : (int)(GS_STAGE_BYTES / ((size_t)K * 4));
+    if (P < 1) P = 1;
+    if (P > 8) P = 8;
     const int npairs = N >> 1;
     int grid = sm_count();
     if (grid > npairs) grid = npairs;
     kern<<<grid, GS_THREADS, smem, st>>>((const bf16*)x, (const bf16*)W, (bf16*)y, N, K, (const bf16*)bias,
-                                         (const bf16*)residual, (const bf16*)norm_w, eps, flags, KC, n_stages);
+                                         (const bf16*)residual, (const bf16*)norm_w, eps, flags, P, n_stages);
     return check_launch("tl_gemv_bf16/stream");
 }
 
