@@ -111,6 +111,40 @@ int tl_advance_pos(int32_t* pos_dev, int32_t* kv_len_dev, int delta, void* strea
  * (replaces the per-token TOKEN packet, tensorlink/p2p/torch_node.py:543-551) */
 int tl_append_token(const int64_t* ids, int64_t* out_tokens, int32_t* step_dev, int B, int ld, void* stream);
 
+/* ---- training-only pieces (K8/K9/K10): replace the autograd graph of `assoc_output.backward(loss)`
+ * (tensorlink/ml/worker.py:271) and `optimizer.step()` (tensorlink/ml/worker.py:1317) ------------------------- */
+/* SwiGLU on interleaved gate/up pre-activations gu[M,2I] (col 2j = gate_j, 2j+1 = up_j): h[M,I], HF rounding */
+int tl_swiglu_fwd(const void* gu, void* h, int M, int I, void* stream);
+/* dgu[M,2I] from dh[M,I] */
+int tl_swiglu_bwd(const void* gu, const void* dh, void* dgu, int M, int I, void* stream);
+/* RMSNorm backward: dx = rstd*(dy*w - n*mean(dy*w*n)) (+ dx_add if non-NULL); dw_accum (fp32 [H]) += sum dy*n */
+int tl_rmsnorm_bwd(const void* x, const void* w, const void* dy, const float* rstd, const void* dx_add, void* dx,
+                   float* dw_accum, int rows, int H, void* stream);
+/* RoPE backward + KV gather: dqkv[n, (n_h+2n_kv)*d] from dq[n, n_h*d] and dk/dv[B, n_kv, T_max, d] */
+int tl_rope_kv_bwd(const void* dq, const void* dk, const void* dv, void* dqkv, const void* cos_tab,
+                   const void* sin_tab, int n_tokens, int S, int n_h, int n_kv, int d, int T_max, void* stream);
+/* attention backward (recompute P from lse): dq[B,S,n_h,d]; dk/dv[B,n_kv,T_max,d] rows < S */
+size_t tl_attn_bwd_ws(int B, int S, int n_h);
+int tl_attn_bwd(const void* q, const void* k_cache, const void* v_cache, const void* out, const void* dout,
+                const float* lse, void* dq, void* dk, void* dv, void* workspace, size_t ws_bytes, int B, int S,
+                int n_h, int n_kv, int d, int T_max, float scale, void* stream);
+/* cross-entropy on bf16 logits[M,V] (fp32 math): *loss_sum += sum_rows (lse - logit[label]); *n_valid += rows
+ * with a valid label; dlogits = (softmax - onehot) * grad_scale (may alias logits); label outside [0,V) ignored */
+int tl_ce_fwd_bwd(const void* logits, const int64_t* labels, float* loss_sum, int32_t* n_valid, void* dlogits,
+                  float grad_scale, int M, int V, void* stream);
+/* embedding backward: dtable[ids[n],:] += dout[n,:]  (bf16x2 atomics into the bf16 gradient) */
+int tl_embed_bwd(const int64_t* ids, const void* dout, void* dtable, int n_tokens, int H, int vocab, void* stream);
+/* bias gradient: db[N] (+)= sum_m dy[m,:N] (row pitch ld) */
+int tl_colsum(const void* dy, void* db, int M, int N, int ld, int accumulate, void* stream);
+/* dst[n] (+)= src[n]: fp32 accumulator into a bf16 gradient */
+int tl_f32_to_bf16_accum(const float* src, void* dst, size_t n, int accumulate, void* stream);
+/* a[n] += b[n] over bf16 (n %% 8 == 0) */
+int tl_add_inplace(void* a, const void* b, size_t n, void* stream);
+/* fused Adam / AdamW (torch.optim update rule, fp32 math and moments) over a flat bf16 parameter arena */
+int tl_adamw_step(void* param, const void* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int step, int decoupled,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

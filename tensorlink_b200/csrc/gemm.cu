@@ -376,8 +376,9 @@ extern "C" int tl_gemm_bf16(const void* A, const void* B, void* C, int M, int N,
                             const void* bias, const void* residual, int flags, void* stream) {
     using namespace tl;
     TL_REQUIRE(M > 0 && N > 0 && K > 0, TL_ERR_INVALID, "tl_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
-    TL_REQUIRE(K % 8 == 0 && N % 8 == 0, TL_ERR_INVALID, "tl_gemm_bf16: N and K must be multiples of 8 (N=%d K=%d)",
-               N, K);
+    TL_REQUIRE(N % 8 == 0, TL_ERR_INVALID, "tl_gemm_bf16: N must be a multiple of 8 (N=%d)", N);
+    TL_REQUIRE(K % 8 == 0 || ((flags & TL_A_MN_MAJOR) && (flags & TL_B_MN_MAJOR)), TL_ERR_INVALID,
+               "tl_gemm_bf16: K must be a multiple of 8 for K-major operands (K=%d)", K);
     TL_REQUIRE(!(flags & TL_EPI_BIAS) || bias, TL_ERR_INVALID, "tl_gemm_bf16: BIAS flag without bias pointer");
     TL_REQUIRE(!(flags & TL_EPI_RESIDUAL) || residual, TL_ERR_INVALID, "tl_gemm_bf16: RESIDUAL flag without pointer");
     const bool swiglu = flags & TL_EPI_SWIGLU;

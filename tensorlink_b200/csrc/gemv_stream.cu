@@ -27,7 +27,7 @@ template <int M>
 __global__ void __launch_bounds__(GS_THREADS, 1)
 gemv_stream_kernel(const bf16* __restrict__ x, const bf16* __restrict__ W, bf16* __restrict__ y, int N, int K,
                    const bf16* __restrict__ bias, const bf16* __restrict__ residual, const bf16* __restrict__ norm_w,
-                   float eps, int flags, int P, int n_stages) {
+                   float eps, int flags, int P, int n_stages, int NW) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* ring = smem;                                                    // [n_stages][GS_STAGE_BYTES]
     bf16* xs = reinterpret_cast<bf16*>(smem + (size_t)n_stages * GS_STAGE_BYTES);  // [M][K]
@@ -40,7 +40,9 @@ gemv_stream_kernel(const bf16* __restrict__ x, const bf16* __restrict__ W, bf16*
     const int p_begin = (int)((long long)blockIdx.x * npairs / gridDim.x);
     const int p_end = (int)((long long)(blockIdx.x + 1) * npairs / gridDim.x);
     const int n_units = (p_end - p_begin + P - 1) / P;                 // unit = P consecutive pairs
-    const int n_groups = (n_units + GS_CONSUMER_WARPS - 1) / GS_CONSUMER_WARPS;
+    // NW consumer warps take units; n_stages %% NW == 0, so ring slot s is ALWAYS consumed by warp s %% NW and every
+    // waiter observes every phase of the barriers it waits on (no mbarrier parity aliasing).
+    const int n_groups = (n_units + NW - 1) / NW;
     const bool chunked = K > GS_KC || (size_t)K * 4 > GS_STAGE_BYTES;  // a pair does not fit one stage
     const int KC = chunked ? GS_KC : K;
     const int n_chunks = (K + KC - 1) / KC;
@@ -61,8 +63,8 @@ gemv_stream_kernel(const bf16* __restrict__ x, const bf16* __restrict__ W, bf16*
             uint32_t phase = 0;
             for (int g = 0; g < n_groups; ++g) {
                 for (int c = 0; c < n_chunks; ++c) {
-                    for (int w = 0; w < GS_CONSUMER_WARPS; ++w) {
-                        const int unit = g * GS_CONSUMER_WARPS + w;
+                    for (int w = 0; w < NW; ++w) {
+                        const int unit = g * NW + w;
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         unsigned char* dst = ring + (size_t)stage * GS_STAGE_BYTES;
                         if (unit >= n_units) {
@@ -192,14 +194,14 @@ gemv_stream_kernel(const bf16* __restrict__ x, const bf16* __restrict__ W, bf16*
         };
         // this warp's stages are sequence numbers warp, warp+8, warp+16, ... of the producer's order
         int seq = warp;
-        for (int g = 0; g < n_groups; ++g) {
-            const int unit = g * GS_CONSUMER_WARPS + warp;
+        for (int g = 0; g < (warp < NW ? n_groups : 0); ++g) {
+            const int unit = g * NW + warp;
             const bool valid = unit < n_units;
             const int pair0 = p_begin + unit * P;
             float a0[M], a1[M];
 #pragma unroll
             for (int m = 0; m < M; ++m) a0[m] = a1[m] = 0.f;
-            for (int c = 0; c < n_chunks; ++c, seq += GS_CONSUMER_WARPS) {
+            for (int c = 0; c < n_chunks; ++c, seq += NW) {
                 const int stage = seq % n_stages;
                 const uint32_t phase = (uint32_t)(seq / n_stages) & 1u;
                 mbar_wait(&full_bar[stage], phase);
@@ -248,9 +250,15 @@ static int launch_stream(const void* x, const void* W, void* y, int N, int K, co
     }
     const size_t xs_bytes = (((size_t)M * K * 2) + 15) & ~(size_t)15;
     const size_t fixed = xs_bytes + 2 * GS_MAX_STAGES * sizeof(uint64_t);
-    int n_stages = (int)((SMEM_CAP - fixed) / GS_STAGE_BYTES);
-    if (n_stages > GS_MAX_STAGES) n_stages = GS_MAX_STAGES;
-    if (n_stages < 3) return 1;   // caller falls back to the register-streaming kernel
+    int max_stages = (int)((SMEM_CAP - fixed) / GS_STAGE_BYTES);
+    if (max_stages > GS_MAX_STAGES) max_stages = GS_MAX_STAGES;
+    if (max_stages < 4) return 1;   // caller falls back to the register-streaming kernel
+    // pick (n_stages, NW): n_stages a multiple of NW, as many bytes in flight as possible, then as many warps
+    int n_stages = 0, NW = 0;
+    for (int nw = GS_CONSUMER_WARPS; nw >= 4; --nw) {
+        const int st = max_stages / nw * nw;
+        if (st > n_stages) { n_stages = st; NW = nw; }
+    }
     const size_t smem = (size_t)n_stages * GS_STAGE_BYTES + fixed;
     const bool chunked = K > GS_KC || (size_t)K * 4 > GS_STAGE_BYTES;
     int P = chunked ? 1 : (int)(GS_STAGE_BYTES / ((size_t)K * 4));
@@ -260,7 +268,7 @@ static int launch_stream(const void* x, const void* W, void* y, int N, int K, co
     int grid = sm_count();
     if (grid > npairs) grid = npairs;
     kern<<<grid, GS_THREADS, smem, st>>>((const bf16*)x, (const bf16*)W, (bf16*)y, N, K, (const bf16*)bias,
-                                         (const bf16*)residual, (const bf16*)norm_w, eps, flags, P, n_stages);
+                                         (const bf16*)residual, (const bf16*)norm_w, eps, flags, P, n_stages, NW);
     return check_launch("tl_gemv_bf16/stream");
 }
 

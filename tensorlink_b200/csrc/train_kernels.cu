@@ -1,0 +1,416 @@
+// Training-only HBM-bound kernels (K8/K9/K10 of SURVEY.md §2.4): SwiGLU fwd/bwd on interleaved gate/up
+// pre-activations, RMSNorm backward, RoPE(+KV scatter) backward, shifted cross-entropy forward+backward,
+// embedding backward, bias column sums, gradient accumulation and a fused AdamW step.
+// They replace the autograd graph of unfused ATen ops the reference's worker runs in
+// `assoc_output.backward(loss)` (/root/reference/tensorlink/ml/worker.py:271) and its `optimizer.step()` (:1317).
+#include "common.cuh"
+
+namespace tl {
+
+// ------------------------------------------------------------------------------------------------ SwiGLU
+// gu[M, 2I] interleaved (2j = gate_j, 2j+1 = up_j)  ->  h[M, I] = bf16(bf16(silu(g)) * u)     (HF rounding)
+__global__ void swiglu_fwd_kernel(const uint4* __restrict__ gu, uint2* __restrict__ h, size_t n_vec) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = gu[i];          // 4 (gate, up) pairs
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(&v);
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = rbf(silu_f(bf16_lo(p[j]))) * bf16_hi(p[j]);
+        h[i] = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
+    }
+}
+
+// dgu from dh:  d_gate = dh * u * silu'(g),  d_up = dh * silu(g);  silu'(g) = s + g*s*(1-s), s = sigmoid(g)
+__global__ void swiglu_bwd_kernel(const uint4* __restrict__ gu, const uint2* __restrict__ dh, uint4* __restrict__ dgu,
+                                  size_t n_vec) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = gu[i];
+        const uint2 d = dh[i];
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(&v);
+        const float dd[4] = {bf16_lo(d.x), bf16_hi(d.x), bf16_lo(d.y), bf16_hi(d.y)};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float g = bf16_lo(p[j]), u = bf16_hi(p[j]);
+            const float s = 1.0f / (1.0f + expf(-g));
+            const float act = rbf(g * s);                          // the bf16 silu(g) the forward multiplied by
+            const float dact = rbf(dd[j] * u);                     // grad wrt silu output (bf16 like autograd)
+            o[j] = pack_bf16(dact * (s + g * s * (1.0f - s)), dd[j] * act);
+        }
+        dgu[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ RMSNorm backward
+// n = x*rstd, g = dy*w:  dx = rstd * (g - n * mean(g*n)) [+ dx_add];  dw[h] += sum_rows dy*n   (fp32 atomics)
+constexpr int NB_THREADS = 128, NB_MAXV = 8;
+__global__ void __launch_bounds__(NB_THREADS) rmsnorm_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                                                   const bf16* __restrict__ dy, const float* __restrict__ rstd,
+                                                                   const bf16* __restrict__ dx_add, bf16* __restrict__ dx,
+                                                                   float* __restrict__ dw_accum, int rows, int H,
+                                                                   int rows_per_block) {
+    const int nvec = H >> 3;
+    float dwl[NB_MAXV][8];
+#pragma unroll
+    for (int i = 0; i < NB_MAXV; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dwl[i][j] = 0.f;
+    __shared__ float red[NB_THREADS / 32];
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    for (int row = r0; row < r1; ++row) {
+        const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * H);
+        const uint4* dr = reinterpret_cast<const uint4*>(dy + (size_t)row * H);
+        const float rs = rstd[row];
+        float nv[NB_MAXV][8], gv[NB_MAXV][8];
+        float dot = 0.f;
+#pragma unroll
+        for (int i = 0; i < NB_MAXV; ++i) {
+            const int idx = threadIdx.x + i * NB_THREADS;
+            if (idx < nvec) {
+                const uint4 xv = xr[idx], dv = dr[idx], wv = reinterpret_cast<const uint4*>(w)[idx];
+                const uint32_t* x32 = reinterpret_cast<const uint32_t*>(&xv);
+                const uint32_t* d32 = reinterpret_cast<const uint32_t*>(&dv);
+                const uint32_t* w32 = reinterpret_cast<const uint32_t*>(&wv);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float n0 = bf16_lo(x32[j]) * rs, n1 = bf16_hi(x32[j]) * rs;
+                    const float d0 = bf16_lo(d32[j]), d1 = bf16_hi(d32[j]);
+                    nv[i][2 * j] = n0; nv[i][2 * j + 1] = n1;
+                    gv[i][2 * j] = d0 * bf16_lo(w32[j]); gv[i][2 * j + 1] = d1 * bf16_hi(w32[j]);
+                    dot += gv[i][2 * j] * n0 + gv[i][2 * j + 1] * n1;
+                    dwl[i][2 * j] += d0 * rbf(n0); dwl[i][2 * j + 1] += d1 * rbf(n1);
+                }
+            }
+        }
+        dot = warp_sum(dot);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+        __syncthreads();
+        float tot = 0.f;
+#pragma unroll
+        for (int i = 0; i < NB_THREADS / 32; ++i) tot += red[i];
+        const float mean = tot / (float)H;
+        uint4* outr = reinterpret_cast<uint4*>(dx + (size_t)row * H);
+#pragma unroll
+        for (int i = 0; i < NB_MAXV; ++i) {
+            const int idx = threadIdx.x + i * NB_THREADS;
+            if (idx < nvec) {
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = rbf(rs * (gv[i][j] - nv[i][j] * mean));
+                if (dx_add) {
+                    const uint4 av = reinterpret_cast<const uint4*>(dx_add + (size_t)row * H)[idx];
+                    const uint32_t* a32 = reinterpret_cast<const uint32_t*>(&av);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { o[2 * j] += bf16_lo(a32[j]); o[2 * j + 1] += bf16_hi(a32[j]); }
+                }
+                outr[idx] = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+            }
+        }
+    }
+    if (dw_accum) {
+#pragma unroll
+        for (int i = 0; i < NB_MAXV; ++i) {
+            const int idx = threadIdx.x + i * NB_THREADS;
+            if (idx < nvec) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) atomicAdd(&dw_accum[idx * 8 + j], dwl[i][j]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ RoPE backward
+// one warp per (token, head): inverse rotation of dq / dk, plain gather of dv -> dqkv[n, (n_h+2n_kv)*d]
+template <int D>
+__global__ void __launch_bounds__(128) rope_kv_bwd_kernel(const bf16* __restrict__ dq, const bf16* __restrict__ dk,
+                                                           const bf16* __restrict__ dv, bf16* __restrict__ dqkv,
+                                                           const bf16* __restrict__ cos_tab, const bf16* __restrict__ sin_tab,
+                                                           int n_tokens, int S, int n_h, int n_kv, int T_max) {
+    constexpr int HALF = D / 2, PAIRS = HALF / 32;
+    const int heads = n_h + 2 * n_kv;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (gw >= n_tokens * heads) return;
+    const int n = gw / heads, h = gw - n * heads;
+    const int b = n / S, pos = n - b * S;
+    bf16* dst = dqkv + (size_t)n * heads * D + (size_t)h * D;
+    const bool is_q = h < n_h, is_k = !is_q && h < n_h + n_kv;
+    const bf16* src = is_q ? dq + (size_t)n * n_h * D + (size_t)h * D
+                           : (is_k ? dk + (((size_t)b * n_kv + (h - n_h)) * T_max + pos) * D
+                                   : dv + (((size_t)b * n_kv + (h - n_h - n_kv)) * T_max + pos) * D);
+#pragma unroll
+    for (int p = 0; p < PAIRS; ++p) {
+        const int i = lane + 32 * p;
+        const float d1 = bf2f(src[i]), d2 = bf2f(src[i + HALF]);
+        if (!is_q && !is_k) {
+            dst[i] = f2bf(d1);
+            dst[i + HALF] = f2bf(d2);
+        } else {
+            const float c = bf2f(cos_tab[(size_t)pos * HALF + i]), s = bf2f(sin_tab[(size_t)pos * HALF + i]);
+            dst[i] = f2bf(d1 * c + d2 * s);
+            dst[i + HALF] = f2bf(d2 * c - d1 * s);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ cross entropy
+// one CTA per row: loss_sum += logsumexp(row) - row[label]; dlogits = (softmax - onehot) * grad_scale (in place ok)
+constexpr int CE_THREADS = 512;
+__global__ void __launch_bounds__(CE_THREADS) ce_fwd_bwd_kernel(const bf16* __restrict__ logits, const int64_t* __restrict__ labels,
+                                                                 float* __restrict__ loss_sum, int32_t* __restrict__ n_valid,
+                                                                 bf16* __restrict__ dlogits, float grad_scale, int V) {
+    const int row = blockIdx.x;
+    const long long label = labels[row];
+    const bf16* lr = logits + (size_t)row * V;
+    bf16* dr = dlogits + (size_t)row * V;
+    const int nvec = V >> 3;
+    __shared__ float red[CE_THREADS / 32];
+    __shared__ float s_bcast;
+    if (label < 0 || label >= V) {      // ignore_index (-100): zero gradient, no loss
+        if (dlogits) for (int i = threadIdx.x; i < nvec; i += CE_THREADS) reinterpret_cast<uint4*>(dr)[i] = make_uint4(0, 0, 0, 0);
+        return;
+    }
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < nvec; i += CE_THREADS) {
+        const uint4 v = reinterpret_cast<const uint4*>(lr)[i];
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mx = fmaxf(mx, fmaxf(bf16_lo(p[j]), bf16_hi(p[j])));
+    }
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = red[0];
+        for (int i = 1; i < CE_THREADS / 32; ++i) m = fmaxf(m, red[i]);
+        s_bcast = m;
+    }
+    __syncthreads();
+    mx = s_bcast;
+    float se = 0.f;
+    for (int i = threadIdx.x; i < nvec; i += CE_THREADS) {
+        const uint4 v = reinterpret_cast<const uint4*>(lr)[i];
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) se += expf(bf16_lo(p[j]) - mx) + expf(bf16_hi(p[j]) - mx);
+    }
+    se = warp_sum(se);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = se;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int i = 0; i < CE_THREADS / 32; ++i) s += red[i];
+        s_bcast = s;
+        const float lse = mx + logf(s);
+        atomicAdd(loss_sum, lse - bf2f(lr[label]));
+        if (n_valid) atomicAdd(n_valid, 1);
+    }
+    __syncthreads();
+    if (!dlogits) return;
+    const float inv = grad_scale / s_bcast;
+    for (int i = threadIdx.x; i < nvec; i += CE_THREADS) {
+        const uint4 v = reinterpret_cast<const uint4*>(lr)[i];
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(&v);
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            o[2 * j] = expf(bf16_lo(p[j]) - mx) * inv;
+            o[2 * j + 1] = expf(bf16_hi(p[j]) - mx) * inv;
+        }
+        const int base = i * 8;
+        if (label >= base && label < base + 8) o[label - base] -= grad_scale;
+        reinterpret_cast<uint4*>(dr)[i] = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ embedding backward
+__global__ void embed_bwd_kernel(const int64_t* __restrict__ ids, const bf16* __restrict__ dout, bf16* __restrict__ dtable,
+                                 int n_tokens, int H, int vocab) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_tokens) return;
+    const long long id = ids[warp];
+    if (id < 0 || id >= vocab) return;
+    const __nv_bfloat162* src = reinterpret_cast<const __nv_bfloat162*>(dout + (size_t)warp * H);
+    __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(dtable + (size_t)id * H);
+    for (int i = lane; i < (H >> 1); i += 32) atomicAdd(&dst[i], src[i]);
+}
+
+// ------------------------------------------------------------------------------------------------ column sum (bias grad)
+// db[c] (+)= sum_m dy[m, c];  block = 32x8 threads handles 64 columns (bf16x2 per thread.x), rows strided over y
+__global__ void colsum_kernel(const bf16* __restrict__ dy, bf16* __restrict__ db, int M, int N, int ld, int accumulate) {
+    const int c2 = blockIdx.x * 32 + threadIdx.x;      // bf16x2 column index
+    float a0 = 0.f, a1 = 0.f;
+    if (2 * c2 < N) {
+        for (int m = blockIdx.y * blockDim.y + threadIdx.y; m < M; m += gridDim.y * blockDim.y) {
+            const uint32_t u = *reinterpret_cast<const uint32_t*>(dy + (size_t)m * ld + 2 * c2);
+            a0 += bf16_lo(u);
+            a1 += bf16_hi(u);
+        }
+    }
+    __shared__ float s0[8][33], s1[8][33];
+    s0[threadIdx.y][threadIdx.x] = a0;
+    s1[threadIdx.y][threadIdx.x] = a1;
+    __syncthreads();
+    if (threadIdx.y == 0 && 2 * c2 < N) {
+#pragma unroll
+        for (int j = 1; j < 8; ++j) { a0 += s0[j][threadIdx.x]; a1 += s1[j][threadIdx.x]; }
+        // gridDim.y partial sums are combined with fp32 atomics on a scratch-free path: gridDim.y == 1 by launch
+        if (accumulate) {
+            a0 += bf2f(db[2 * c2]);
+            a1 += bf2f(db[2 * c2 + 1]);
+        }
+        *reinterpret_cast<uint32_t*>(db + 2 * c2) = pack_bf16(a0, a1);
+    }
+}
+
+// fp32 accumulator -> bf16 gradient (+=)
+__global__ void f32_to_bf16_accum_kernel(const float* __restrict__ src, bf16* __restrict__ dst, size_t n, int accumulate) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = f2bf(src[i] + (accumulate ? bf2f(dst[i]) : 0.f));
+}
+
+__global__ void add_inplace_kernel(uint4* __restrict__ a, const uint4* __restrict__ b, size_t n_vec) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * blockDim.x) {
+        uint4 x = a[i];
+        const uint4 y = b[i];
+        uint32_t* x32 = reinterpret_cast<uint32_t*>(&x);
+        const uint32_t* y32 = reinterpret_cast<const uint32_t*>(&y);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x32[j] = pack_bf16(bf16_lo(x32[j]) + bf16_lo(y32[j]), bf16_hi(x32[j]) + bf16_hi(y32[j]));
+        a[i] = x;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ AdamW
+// torch.optim.Adam/AdamW update rule in fp32 on bf16 parameters, fp32 moments
+__global__ void adamw_kernel(bf16* __restrict__ p, const bf16* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                             size_t n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
+                             int decoupled) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float pw = bf2f(p[i]), gr = bf2f(g[i]);
+        if (wd != 0.f) {
+            if (decoupled) pw *= (1.0f - lr * wd);
+            else gr += wd * pw;
+        }
+        const float mi = b1 * m[i] + (1.0f - b1) * gr;
+        const float vi = b2 * v[i] + (1.0f - b2) * gr * gr;
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = f2bf(pw - (lr / bc1) * (mi / denom));
+    }
+}
+
+static inline int ew_grid(size_t n, int threads) {
+    size_t b = (n + threads - 1) / threads;
+    const size_t cap = (size_t)sm_count() * 16;
+    return (int)(b < cap ? (b ? b : 1) : cap);
+}
+
+}  // namespace tl
+
+extern "C" {
+
+int tl_swiglu_fwd(const void* gu, void* h, int M, int I, void* stream) {
+    using namespace tl;
+    TL_REQUIRE(I % 4 == 0, TL_ERR_INVALID, "tl_swiglu_fwd: I %% 4 != 0");
+    const size_t n_vec = (size_t)M * I / 4;
+    if (!n_vec) return TL_OK;
+    swiglu_fwd_kernel<<<ew_grid(n_vec, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)gu, (uint2*)h, n_vec);
+    return check_launch("tl_swiglu_fwd");
+}
+
+int tl_swiglu_bwd(const void* gu, const void* dh, void* dgu, int M, int I, void* stream) {
+    using namespace tl;
+    TL_REQUIRE(I % 4 == 0, TL_ERR_INVALID, "tl_swiglu_bwd: I %% 4 != 0");
+    const size_t n_vec = (size_t)M * I / 4;
+    if (!n_vec) return TL_OK;
+    swiglu_bwd_kernel<<<ew_grid(n_vec, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)gu, (const uint2*)dh, (uint4*)dgu, n_vec);
+    return check_launch("tl_swiglu_bwd");
+}
+
+int tl_rmsnorm_bwd(const void* x, const void* w, const void* dy, const float* rstd, const void* dx_add, void* dx,
+                   float* dw_accum, int rows, int H, void* stream) {
+    using namespace tl;
+    TL_REQUIRE(H % 8 == 0 && H <= NB_THREADS * NB_MAXV * 8, TL_ERR_INVALID, "tl_rmsnorm_bwd: unsupported H=%d", H);
+    if (rows == 0) return TL_OK;
+    int rpb = (rows + sm_count() * 4 - 1) / (sm_count() * 4);
+    if (rpb < 1) rpb = 1;
+    const int grid = (rows + rpb - 1) / rpb;
+    rmsnorm_bwd_kernel<<<grid, NB_THREADS, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)w, (const bf16*)dy, rstd,
+                                                                      (const bf16*)dx_add, (bf16*)dx, dw_accum, rows, H, rpb);
+    return check_launch("tl_rmsnorm_bwd");
+}
+
+int tl_rope_kv_bwd(const void* dq, const void* dk, const void* dv, void* dqkv, const void* cos_tab, const void* sin_tab,
+                   int n_tokens, int S, int n_h, int n_kv, int d, int T_max, void* stream) {
+    using namespace tl;
+    TL_REQUIRE(d == 64 || d == 128, TL_ERR_INVALID, "tl_rope_kv_bwd: head_dim %d not in {64,128}", d);
+    if (n_tokens == 0) return TL_OK;
+    const long long warps = (long long)n_tokens * (n_h + 2 * n_kv);
+    const int grid = (int)((warps + 3) / 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d == 64)
+        rope_kv_bwd_kernel<64><<<grid, 128, 0, st>>>((const bf16*)dq, (const bf16*)dk, (const bf16*)dv, (bf16*)dqkv,
+                                                     (const bf16*)cos_tab, (const bf16*)sin_tab, n_tokens, S, n_h, n_kv, T_max);
+    else
+        rope_kv_bwd_kernel<128><<<grid, 128, 0, st>>>((const bf16*)dq, (const bf16*)dk, (const bf16*)dv, (bf16*)dqkv,
+                                                      (const bf16*)cos_tab, (const bf16*)sin_tab, n_tokens, S, n_h, n_kv, T_max);
+    return check_launch("tl_rope_kv_bwd");
+}
+
+int tl_ce_fwd_bwd(const void* logits, const int64_t* labels, float* loss_sum, int32_t* n_valid, void* dlogits,
+                  float grad_scale, int M, int V, void* stream) {
+    using namespace tl;
+    TL_REQUIRE(V % 8 == 0, TL_ERR_INVALID, "tl_ce_fwd_bwd: V %% 8 != 0");
+    if (M == 0) return TL_OK;
+    ce_fwd_bwd_kernel<<<M, CE_THREADS, 0, (cudaStream_t)stream>>>((const bf16*)logits, labels, loss_sum, n_valid, (bf16*)dlogits,
+                                                                  grad_scale, V);
+    return check_launch("tl_ce_fwd_bwd");
+}
+
+int tl_embed_bwd(const int64_t* ids, const void* dout, void* dtable, int n_tokens, int H, int vocab, void* stream) {
+    using namespace tl;
+    TL_REQUIRE(H % 2 == 0, TL_ERR_INVALID, "tl_embed_bwd: H odd");
+    if (n_tokens == 0) return TL_OK;
+    embed_bwd_kernel<<<(n_tokens + 7) / 8, 256, 0, (cudaStream_t)stream>>>(ids, (const bf16*)dout, (bf16*)dtable, n_tokens, H, vocab);
+    return check_launch("tl_embed_bwd");
+}
+
+int tl_colsum(const void* dy, void* db, int M, int N, int ld, int accumulate, void* stream) {
+    using namespace tl;
+    TL_REQUIRE(N % 2 == 0 && ld % 2 == 0, TL_ERR_INVALID, "tl_colsum: N/ld must be even");
+    const dim3 grid((N / 2 + 31) / 32, 1), block(32, 8);
+    colsum_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const bf16*)dy, (bf16*)db, M, N, ld, accumulate);
+    return check_launch("tl_colsum");
+}
+
+int tl_f32_to_bf16_accum(const float* src, void* dst, size_t n, int accumulate, void* stream) {
+    using namespace tl;
+    if (!n) return TL_OK;
+    f32_to_bf16_accum_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n, accumulate);
+    return check_launch("tl_f32_to_bf16_accum");
+}
+
+int tl_add_inplace(void* a, const void* b, size_t n, void* stream) {
+    using namespace tl;
+    TL_REQUIRE(n % 8 == 0, TL_ERR_INVALID, "tl_add_inplace: n %% 8 != 0");
+    if (!n) return TL_OK;
+    add_inplace_kernel<<<ew_grid(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((uint4*)a, (const uint4*)b, n / 8);
+    return check_launch("tl_add_inplace");
+}
+
+int tl_adamw_step(void* param, const void* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int step, int decoupled, void* stream) {
+    using namespace tl;
+    TL_REQUIRE(step >= 1, TL_ERR_INVALID, "tl_adamw_step: step must start at 1");
+    if (!n) return TL_OK;
+    const float bc1 = 1.0f - powf(beta1, (float)step);
+    const float bc2s = sqrtf(1.0f - powf(beta2, (float)step));
+    adamw_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>((bf16*)param, (const bf16*)grad, exp_avg, exp_avg_sq, n, lr,
+                                                                    beta1, beta2, eps, weight_decay, bc1, bc2s, decoupled);
+    return check_launch("tl_adamw_step");
+}
+
+}  // extern "C"

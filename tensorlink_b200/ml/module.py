@@ -173,19 +173,20 @@ class DistributedModel(torch.nn.Module):
             x = st.embed(input_ids.to(self.device))
         else:
             x = torch.empty(B, S, cfg.hidden, dtype=torch.bfloat16, device=self.device)
-            link.recv(x, link.prev)
+            link.recv_prev(x)
         x = st.prefill(x, 0, 0)
         if not link.last:
-            link.send(x.contiguous(), link.next)
+            link.send_next(x.clone())
             logits = None
         else:
             logits = st.head_logits(x.reshape(B * S, cfg.hidden)).view(B, S, cfg.vocab)
         if gather and self.world > 1:
             if link.last:
-                link.send(logits.contiguous(), 0)
+                link.send_up(logits.contiguous(), 0)
             elif link.first:
                 logits = torch.empty(B, S, cfg.vocab, dtype=torch.bfloat16, device=self.device)
-                link.recv(logits, self.world - 1)
+                link.recv_up(logits, self.world - 1)
+        link.flush()
         return CausalLMOutput(logits=logits)
 
     # ------------------------------------------------------------------------------------------ generate
@@ -217,43 +218,51 @@ class DistributedModel(torch.nn.Module):
         ids_rows = [input_ids[m * b:(m + 1) * b].to(dev) for m in range(n_mb)] if link.first else [None] * n_mb
 
         # ---- prefill every micro-batch through the pipeline; the last stage produces the first new token
-        xbuf = [torch.empty(b, S, cfg.hidden, dtype=torch.bfloat16, device=dev) for _ in range(n_mb)] \
-            if not link.first else None
+        multi = self.world > 1
         for m in range(n_mb):
-            x = st.embed(ids_rows[m]) if link.first else xbuf[m]
-            if not link.first:
-                link.recv(x, link.prev)
+            if link.first:
+                x = st.embed(ids_rows[m])
+            else:
+                x = torch.empty(b, S, cfg.hidden, dtype=torch.bfloat16, device=dev)
+                link.recv_prev(x)
             x = st.prefill(x, 0, m)
             if not link.last:
-                link.send(x.contiguous(), link.next)
+                link.send_next(x.clone())
             else:
                 st.head_argmax(x[:, -1, :].contiguous(), st.ids_dec[m][:b])
-                if self.world > 1:
-                    link.send(st.ids_dec[m][:b], 0)
-        # ---- decode rounds: micro-batches rotate through the stages; hidden [b,H] hops forward, ids hop back
+                if multi:
+                    link.send_up(st.ids_dec[m][:b].clone(), 0)
+        # ---- decode rounds: micro-batches rotate through the stages; hidden [b,H] hops down, ids hop back up.
+        # Sends are asynchronous; a slot's buffer is waited on only right before the next step overwrites it.
+        sent_x = [None] * n_mb
+        sent_ids = [None] * n_mb
         for step in range(max_new):
             for m in range(n_mb):
                 if link.first:
-                    if self.world > 1:
-                        link.recv(st.ids_dec[m][:b], self.world - 1)
+                    if multi:
+                        link.wait(sent_x[m])                       # x_dec[m] still feeding the previous hop?
+                        link.recv_up(st.ids_dec[m][:b], self.world - 1)
                     out_tokens[m * b:(m + 1) * b, step] = st.ids_dec[m][:b]
                     if streamer is not None and n_mb == 1:
                         streamer.put(st.ids_dec[m][:b].cpu())
                 if step == max_new - 1:
                     continue
                 if not link.first:
-                    link.recv(st.x_dec[m][:b], link.prev)
+                    link.wait(sent_x[m])
+                    link.recv_prev(st.x_dec[m][:b])
+                if link.last and multi:
+                    link.wait(sent_ids[m])
                 st.decode(m, b, use_graph)
                 if not link.last:
-                    link.send(st.x_dec[m][:b], link.next)
-                elif self.world > 1:
-                    link.send(st.ids_dec[m][:b], 0)
+                    sent_x[m] = link.send_next(st.x_dec[m][:b])
+                elif multi:
+                    sent_ids[m] = link.send_up(st.ids_dec[m][:b], 0)
+        link.flush()
         if link.first:
             result = torch.cat([input_ids.to(dev), out_tokens], dim=1)
         else:
             result = torch.empty(B, S + max_new, dtype=torch.int64, device=dev)
-        if self.world > 1:
-            torch.distributed.broadcast(result, src=0, group=link.group)
+        link.broadcast(result, 0)
         if streamer is not None and link.first:
             streamer.end()
         self.timers["generate_wall_s"] = time.perf_counter() - t0

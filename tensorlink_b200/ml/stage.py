@@ -25,6 +25,7 @@ class CudaStage:
         self.cfg = cfg
         self.device = torch.device(device)
         self.has_embed, self.has_head = has_embed, has_head
+        self.supports_training, self.trainer = bool(training), None
         self.params = ShardParams(cfg, layer_ids, has_embed, has_head, self.device, with_grad=training)
         if state_dict is not None:
             self.params.load_hf_state_dict(state_dict)
@@ -112,7 +113,6 @@ class CudaStage:
 
     def n_decode_launches(self, B: int) -> int:
         """Kernel launches inside one decode step of this stage (for bench.py's gpu_launches claim)."""
-        per_layer = 9 if B <= 8 else 11   # gemv x4 (+norm fused) / rope / attn split+reduce / 2 advance amortised
         n = len(self.slots[0].layer_ids) * (7 if B <= 8 else 9) + 2
         if self.has_embed:
             n += 1

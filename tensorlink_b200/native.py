@@ -46,6 +46,21 @@ _SIGS = {
     "tl_argmax_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "tl_advance_pos": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "tl_append_token": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "tl_swiglu_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "tl_swiglu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "tl_rmsnorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                               c_void_p]),
+    "tl_rope_kv_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                               c_int, c_int, c_void_p]),
+    "tl_attn_bwd_ws": (c_size_t, [c_int, c_int, c_int]),
+    "tl_attn_bwd": (c_int, [c_void_p] * 10 + [c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "tl_ce_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p]),
+    "tl_embed_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "tl_colsum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "tl_f32_to_bf16_accum": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    "tl_add_inplace": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tl_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float, c_float, c_float,
+                              c_float, c_int, c_int, c_void_p]),
 }
 
 _lib: Optional[ctypes.CDLL] = None
@@ -251,3 +266,76 @@ def append_token(ids, out_tokens, step_dev):
     assert ids.dtype == torch.int64 and out_tokens.dtype == torch.int64 and out_tokens.is_contiguous()
     B, ld = out_tokens.shape
     _check(load().tl_append_token(_p(ids), _p(out_tokens), _p(step_dev), B, ld, _stream()), "tl_append_token")
+
+
+# ------------------------------------------------------------------------------------------ training wrappers
+def swiglu_fwd(gu, h):
+    require_device(); _bf16(gu, h)
+    M, I = h.shape
+    _check(load().tl_swiglu_fwd(_p(gu), _p(h), M, I, _stream()), "tl_swiglu_fwd")
+
+
+def swiglu_bwd(gu, dh, dgu):
+    require_device(); _bf16(gu, dh, dgu)
+    M, I = dh.shape
+    _check(load().tl_swiglu_bwd(_p(gu), _p(dh), _p(dgu), M, I, _stream()), "tl_swiglu_bwd")
+
+
+def rmsnorm_bwd(x, w, dy, rstd, dx, dw_accum, dx_add=None):
+    require_device(); _bf16(x, w, dy, dx, dx_add)
+    H = x.shape[-1]
+    _check(load().tl_rmsnorm_bwd(_p(x), _p(w), _p(dy), _p(rstd), _p(dx_add), _p(dx), _p(dw_accum), x.numel() // H, H,
+                                 _stream()), "tl_rmsnorm_bwd")
+
+
+def rope_kv_bwd(dq, dk, dv, dqkv, cos_tab, sin_tab, S, n_h, n_kv, d):
+    require_device(); _bf16(dq, dk, dv, dqkv)
+    _check(load().tl_rope_kv_bwd(_p(dq), _p(dk), _p(dv), _p(dqkv), _p(cos_tab), _p(sin_tab), dqkv.shape[0], S, n_h, n_kv,
+                                 d, dk.shape[2], _stream()), "tl_rope_kv_bwd")
+
+
+def attn_bwd_ws(B, S, n_h) -> int:
+    return int(load().tl_attn_bwd_ws(B, S, n_h))
+
+
+def attn_bwd(q, k_cache, v_cache, out, dout, lse, dq, dk, dv, ws, B, S, n_h, n_kv, d, scale):
+    require_device(); _bf16(q, k_cache, v_cache, out, dout, dq, dk, dv)
+    _check(load().tl_attn_bwd(_p(q), _p(k_cache), _p(v_cache), _p(out), _p(dout), _p(lse), _p(dq), _p(dk), _p(dv), _p(ws),
+                              ws.numel() * ws.element_size(), B, S, n_h, n_kv, d, k_cache.shape[2], scale, _stream()),
+           "tl_attn_bwd")
+
+
+def ce_fwd_bwd(logits, labels, loss_sum, n_valid, dlogits, grad_scale: float):
+    require_device(); _bf16(logits, dlogits)
+    M, V = logits.shape
+    assert labels.dtype == torch.int64 and loss_sum.dtype == torch.float32
+    _check(load().tl_ce_fwd_bwd(_p(logits), _p(labels), _p(loss_sum), _p(n_valid), _p(dlogits), grad_scale, M, V,
+                                _stream()), "tl_ce_fwd_bwd")
+
+
+def embed_bwd(ids, dout, dtable):
+    require_device(); _bf16(dout, dtable)
+    V, H = dtable.shape
+    _check(load().tl_embed_bwd(_p(ids), _p(dout), _p(dtable), ids.numel(), H, V, _stream()), "tl_embed_bwd")
+
+
+def colsum(dy, db, accumulate: bool):
+    require_device(); _bf16(db)
+    M, N = dy.shape
+    _check(load().tl_colsum(_p(dy), _p(db), M, N, dy.stride(0), int(accumulate), _stream()), "tl_colsum")
+
+
+def f32_to_bf16_accum(src, dst, accumulate: bool):
+    require_device()
+    _check(load().tl_f32_to_bf16_accum(_p(src), _p(dst), src.numel(), int(accumulate), _stream()), "tl_f32_to_bf16_accum")
+
+
+def add_inplace(a, b):
+    require_device(); _bf16(a, b)
+    _check(load().tl_add_inplace(_p(a), _p(b), a.numel(), _stream()), "tl_add_inplace")
+
+
+def adamw_step(param, grad, m, v, lr, beta1, beta2, eps, wd, step: int, decoupled: bool):
+    require_device()
+    _check(load().tl_adamw_step(_p(param), _p(grad), _p(m), _p(v), param.numel(), lr, beta1, beta2, eps, wd, step,
+                                int(decoupled), _stream()), "tl_adamw_step")

@@ -7,11 +7,17 @@ What this replaces (paths under /root/reference/tensorlink):
     (p2p/torch_node.py:825-836, :251-299, :865-869, :225-249);
   * ``Connection.send/_process_data_chunk`` TCP chunking with the EOT marker and the temp-file spill
     (p2p/connection.py:130-162, :218-264).
-Here a hop is one ``ncclSend``/``ncclRecv`` of the bf16 ``hidden_states`` tensor (or its gradient) rank i -> i±1
-over NVLink, issued through ``torch.distributed`` so it runs on NCCL's own stream and overlaps the next
-micro-batch's kernels on the compute stream; masks, RoPE tables, positions and the KV cache never travel.
-Keys are the reference's ``(n_batch, n_micro, module_id)`` triple reduced to a deterministic schedule, so no
-tag matching is needed.  On CPU (tests) the same code runs over ``gloo``.
+Here a hop is one ``ncclSend``/``ncclRecv`` of the bf16 ``hidden_states`` tensor (or its gradient, or the [B] int64
+token ids) between two ranks over NVLink, issued through ``torch.distributed`` so it runs on NCCL's own stream and
+overlaps the next micro-batch's kernels on the compute stream; masks, RoPE tables, positions and the KV cache never
+travel.  The reference's ``(n_batch, n_micro, module_id)`` message keys become a deterministic schedule, so no tag
+matching is needed.
+
+Two channels (two process groups = two NCCL communicators per rank pair): ``down`` carries activations and labels
+towards higher ranks, ``up`` carries gradients and token ids towards lower ranks.  Within a channel every rank pair
+sees its messages in the same order on both ends, and the two directions never share a stream, so neither a
+host-blocking transport (gloo, CPU tests) nor a stream-blocking one (NCCL) can deadlock on crossed sends.
+All sends are ``isend``; a buffer is waited on only right before it is overwritten.
 """
 from __future__ import annotations
 
@@ -36,11 +42,27 @@ def init_process_group_from_env(backend: Optional[str] = None) -> bool:
     return True
 
 
-class StageLink:
-    """Point-to-point link of one pipeline stage to its neighbours."""
+class SendHandle:
+    """An in-flight ``isend``.  ``wait()`` is idempotent (gloo's send work blocks forever when waited twice) and
+    keeps the tensor alive until then."""
+    __slots__ = ("work", "tensor", "done")
 
-    def __init__(self, rank: int, world: int, group=None):
-        self.rank, self.world, self.group = rank, world, group
+    def __init__(self, work, tensor):
+        self.work, self.tensor, self.done = work, tensor, False
+
+    def wait(self):
+        if not self.done:
+            self.work.wait()
+            self.done, self.tensor = True, None
+
+
+class StageLink:
+    """Point-to-point links of one pipeline stage."""
+
+    def __init__(self, rank: int, world: int, down_group=None, up_group=None):
+        self.rank, self.world = rank, world
+        self.down, self.up = down_group, up_group
+        self.group = down_group
         self.prev = rank - 1 if rank > 0 else None
         self.next = rank + 1 if rank < world - 1 else None
         self.first, self.last = rank == 0, rank == world - 1
@@ -50,43 +72,74 @@ class StageLink:
 
     @classmethod
     def from_env(cls) -> "StageLink":
-        if dist.is_initialized():
-            return cls(dist.get_rank(), dist.get_world_size())
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            ranks = list(range(dist.get_world_size()))
+            down = dist.new_group(ranks)          # collective call: every rank constructs its link at the same point
+            up = dist.new_group(ranks)
+            return cls(dist.get_rank(), dist.get_world_size(), down, up)
         return cls(0, 1)
 
-    # -- asynchronous primitives: return a work handle; .wait() orders the current stream after the transfer
-    def isend(self, t: torch.Tensor, dst: int):
+    # ---- primitives -------------------------------------------------------------------------------------
+    def _isend(self, t: torch.Tensor, dst: int, group):
         self.bytes_sent += t.numel() * t.element_size()
-        w = dist.isend(t, dst, group=self.group)
-        self._pending.append((w, t))          # keep the buffer alive until the send has been consumed
-        if len(self._pending) > 64:
-            self.flush()
-        return w
+        h = SendHandle(dist.isend(t, dst, group=group), t)
+        self._pending.append(h)
+        if len(self._pending) > 256:
+            self._pending = [p for p in self._pending if not p.done]
+        return h
 
-    def irecv(self, t: torch.Tensor, src: int):
+    def _recv(self, t: torch.Tensor, src: int, group):
         self.bytes_recv += t.numel() * t.element_size()
-        return dist.irecv(t, src, group=self.group)
+        dist.irecv(t, src, group=group).wait()  # NCCL: orders the compute stream after the transfer; gloo: blocks
 
-    def send(self, t: torch.Tensor, dst: int):
-        self.bytes_sent += t.numel() * t.element_size()
-        dist.send(t, dst, group=self.group)
+    # activations / labels towards higher ranks
+    def send_next(self, t: torch.Tensor):
+        return self._isend(t, self.next, self.down)
 
-    def recv(self, t: torch.Tensor, src: int):
-        self.bytes_recv += t.numel() * t.element_size()
-        dist.recv(t, src, group=self.group)
+    def recv_prev(self, t: torch.Tensor):
+        self._recv(t, self.prev, self.down)
+
+    def send_down(self, t: torch.Tensor, dst: int):
+        return self._isend(t, dst, self.down)
+
+    def recv_down(self, t: torch.Tensor, src: int):
+        self._recv(t, src, self.down)
+
+    # gradients / token ids / gathered results towards lower ranks
+    def send_prev(self, t: torch.Tensor):
+        return self._isend(t, self.prev, self.up)
+
+    def recv_next(self, t: torch.Tensor):
+        self._recv(t, self.next, self.up)
+
+    def send_up(self, t: torch.Tensor, dst: int):
+        return self._isend(t, dst, self.up)
+
+    def recv_up(self, t: torch.Tensor, src: int):
+        self._recv(t, src, self.up)
+
+    # ---- housekeeping -----------------------------------------------------------------------------------
+    @staticmethod
+    def wait(work):
+        if work is not None:
+            work.wait()
 
     def flush(self):
-        for w, _ in self._pending:
-            w.wait()
+        for h in self._pending:
+            h.wait()
         self._pending.clear()
 
     def barrier(self):
         if self.world > 1:
-            dist.barrier(group=self.group)
+            dist.barrier(group=self.down)
+
+    def broadcast(self, t: torch.Tensor, src: int):
+        if self.world > 1:
+            dist.broadcast(t, src=src, group=self.down)
 
     def broadcast_object(self, obj, src: int = 0):
         if self.world == 1:
             return obj
         box = [obj]
-        dist.broadcast_object_list(box, src=src, group=self.group)
+        dist.broadcast_object_list(box, src=src, group=self.down)
         return box[0]
