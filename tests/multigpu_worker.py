@@ -1,0 +1,61 @@
+"""Run under torchrun with one B200 per rank (NCCL): pipeline-sharded results must equal the single-stage results
+computed with the same kernels on rank 0's GPU (sharding must not change a bit: same launches, same order)."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from tensorlink_b200.ml import DistributedModel  # noqa: E402
+from tensorlink_b200.ml import configs as C  # noqa: E402
+from tensorlink_b200.ml.weights import synthetic_tokens  # noqa: E402
+from tensorlink_b200.p2p.link import StageLink, init_process_group_from_env  # noqa: E402
+
+
+def main(out_dir):
+    init_process_group_from_env("nccl")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    cfg = C.TINY_QWEN2_D128
+    res = {}
+    single = DistributedModel(cfg, training=False, max_batch=4, max_seq=96, link=StageLink(0, 1)) if rank == 0 else None
+    dm = DistributedModel(cfg, training=False, n_pipelines=2, max_batch=4, max_seq=96)
+    ids = synthetic_tokens(cfg, 4, 20).cuda()
+    out = dm(ids if rank == 0 else None, gather_logits=True)
+    gen = dm.generate(ids if rank == 0 else None, max_new_tokens=24)
+    gen_ng = dm.generate(ids if rank == 0 else None, max_new_tokens=24, use_graph=False)
+    if rank == 0:
+        ref_logits = single(ids).logits
+        single.n_pipelines = 1
+        ref_gen = single.generate(ids, max_new_tokens=24)
+        res["logits_equal"] = bool(torch.equal(out.logits, ref_logits))
+        res["gen_equal"] = bool(torch.equal(gen, ref_gen))
+    res["gen_graph_vs_eager"] = bool(torch.equal(gen, gen_ng))
+    res["bytes_sent_infer"] = dm.link.bytes_sent
+    # training: 2 micro-batches through the 2 stages
+    tids = synthetic_tokens(cfg, 4, 32).cuda()
+    dmt = DistributedModel(cfg, training=True, n_pipelines=2, max_batch=4, max_seq=64, optimizer=torch.optim.Adam)
+    opt = dmt.create_optimizer(lr=1e-3)
+    opt.zero_grad()
+    o = dmt(tids if rank == 0 else None, labels=tids if rank == 0 else None)
+    o.loss.backward()
+    grads = {k: v.cpu() for k, v in dmt.stage.params.hf_state_dict(grads=True).items()}
+    opt.step()
+    res["loss"] = float(o.loss)
+    if rank == 0:
+        st = DistributedModel(cfg, training=True, n_pipelines=2, max_batch=4, max_seq=64, link=StageLink(0, 1),
+                              optimizer=torch.optim.Adam)
+        so = st(tids, labels=tids)
+        so.loss.backward()
+        ref = {k: v.cpu() for k, v in st.stage.params.hf_state_dict(grads=True).items()}
+        res["loss_single"] = float(so.loss)
+        torch.save(ref, os.path.join(out_dir, "ref_grads.pt"))
+    torch.save(grads, os.path.join(out_dir, f"grads{rank}.pt"))
+    torch.save(res, os.path.join(out_dir, f"rank{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])
