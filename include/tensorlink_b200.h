@@ -95,6 +95,12 @@ int tl_attn_decode_fwd(const void* q, const void* k_cache, const void* v_cache, 
                        const int32_t* kv_len_dev, void* workspace, size_t ws_bytes, int B, int n_h, int n_kv,
                        int d, int T_max, float scale, void* stream);
 
+/* ---- K3 + K4 fused for decode, T_max <= 2048: RoPE (+q/k-norm) of the new token, KV-cache append at *pos_dev and
+ * single-pass attention over keys 0..*pos_dev, one launch per layer.  qkv[B, (n_h+2n_kv)*d] post-bias; out[B, n_h*d] */
+int tl_attn_decode_fused(const void* qkv, void* k_cache, void* v_cache, void* out, const int32_t* pos_dev,
+                         const void* cos_tab, const void* sin_tab, const void* q_norm_w, const void* k_norm_w,
+                         float eps, int B, int n_h, int n_kv, int d, int T_max, float scale, void* stream);
+
 /* ---- K7  final norm + lm_head + greedy argmax for M <= 8 rows: ids[m] = argmax_v bf16(norm(x)[m,:]·W[v,:])
  * (lowest index wins ties, as torch.argmax).  logits_out (bf16 [M,V]) optional.
  * workspace >= tl_lmhead_ws(M, V) bytes. */

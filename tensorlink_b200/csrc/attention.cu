@@ -423,3 +423,184 @@ int tl_attn_decode_fwd(const void* q, const void* k_cache, const void* v_cache, 
 }
 
 }  // extern "C"
+
+// ================================================================================================ fused decode
+// RoPE (+ Qwen3 q/k-norm) + KV-cache append + single-pass attention for ONE new token per batch row, short
+// contexts (T_max <= FD_MAX_T).  One CTA per (query head, batch row): the rotated key/value of the new token are
+// recomputed by every head of a GQA group (d multiply-adds) so no CTA has to wait for the cache write of another.
+// Replaces three launches per layer (rope_kv_fwd, attn_decode_split, attn_decode_reduce) at decode time.
+namespace tl {
+
+constexpr int FD_THREADS = 128, FD_MAX_T = 2048;
+
+template <int D>
+__global__ void __launch_bounds__(FD_THREADS) attn_decode_fused_kernel(
+    const bf16* __restrict__ qkv, bf16* __restrict__ k_cache, bf16* __restrict__ v_cache, bf16* __restrict__ out,
+    const int32_t* __restrict__ pos_dev, const bf16* __restrict__ cos_tab, const bf16* __restrict__ sin_tab,
+    const bf16* __restrict__ q_norm_w, const bf16* __restrict__ k_norm_w, float eps, int n_h, int n_kv, int T_max,
+    float scale_log2) {
+    constexpr int HALF = D / 2;
+    const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_rep = n_h / n_kv, kvh = h / n_rep;
+    const int pos = *pos_dev;                       // keys 0..pos-1 are cached; the new token is key `pos`
+    const int heads = n_h + 2 * n_kv;
+    __shared__ __align__(16) float sq[D], sk[D], sv[D];
+    __shared__ float sscore[FD_MAX_T + 1];
+    __shared__ float sred[FD_THREADS / 32];
+    __shared__ float s_bc[2];
+    __shared__ __align__(16) float so[FD_THREADS / 32][D];
+
+    // ---- RoPE of q (head h), k and v of the new token (kv head kvh); identical rounding to rope_kv_fwd_kernel
+    const bf16* row = qkv + (size_t)b * heads * D;
+    float q1 = 0.f, q2 = 0.f, k1 = 0.f, k2 = 0.f;
+    if (tid < HALF) {
+        q1 = bf2f(row[(size_t)h * D + tid]);
+        q2 = bf2f(row[(size_t)h * D + tid + HALF]);
+        k1 = bf2f(row[(size_t)(n_h + kvh) * D + tid]);
+        k2 = bf2f(row[(size_t)(n_h + kvh) * D + tid + HALF]);
+        sv[tid] = bf2f(row[(size_t)(n_h + n_kv + kvh) * D + tid]);
+        sv[tid + HALF] = bf2f(row[(size_t)(n_h + n_kv + kvh) * D + tid + HALF]);
+    }
+    if (q_norm_w) {        // Qwen3: RMSNorm over the head dim (block reduction over the HALF active threads)
+        float a = warp_sum(q1 * q1 + q2 * q2), c = warp_sum(k1 * k1 + k2 * k2);
+        __shared__ float nr[2][FD_THREADS / 32];
+        if (lane == 0) { nr[0][warp] = a; nr[1][warp] = c; }
+        __syncthreads();
+        a = c = 0.f;
+#pragma unroll
+        for (int w = 0; w < FD_THREADS / 32; ++w) { a += nr[0][w]; c += nr[1][w]; }
+        const float rq = 1.0f / sqrtf(a / (float)D + eps), rk = 1.0f / sqrtf(c / (float)D + eps);
+        if (tid < HALF) {
+            q1 = rbf(bf2f(q_norm_w[tid]) * rbf(q1 * rq));
+            q2 = rbf(bf2f(q_norm_w[tid + HALF]) * rbf(q2 * rq));
+            k1 = rbf(bf2f(k_norm_w[tid]) * rbf(k1 * rk));
+            k2 = rbf(bf2f(k_norm_w[tid + HALF]) * rbf(k2 * rk));
+        }
+    }
+    if (tid < HALF) {
+        const float c = bf2f(cos_tab[(size_t)pos * HALF + tid]), s = bf2f(sin_tab[(size_t)pos * HALF + tid]);
+        sq[tid] = rbf(rbf(q1 * c) + rbf(-q2 * s));
+        sq[tid + HALF] = rbf(rbf(q2 * c) + rbf(q1 * s));
+        sk[tid] = rbf(rbf(k1 * c) + rbf(-k2 * s));
+        sk[tid + HALF] = rbf(rbf(k2 * c) + rbf(k1 * s));
+    }
+    __syncthreads();
+    if (h % n_rep == 0 && tid < D) {       // one head of the group appends the new key/value to the cache
+        const size_t off = (((size_t)b * n_kv + kvh) * T_max + pos) * D + tid;
+        k_cache[off] = f2bf(sk[tid]);
+        v_cache[off] = f2bf(sv[tid]);
+    }
+    // ---- scores: one cached key per thread per round; the new key by warp 0
+    const bf16* kb = k_cache + ((size_t)b * n_kv + kvh) * T_max * D;
+    const bf16* vb = v_cache + ((size_t)b * n_kv + kvh) * T_max * D;
+    float mx = -INFINITY;
+    for (int key = tid; key < pos; key += FD_THREADS) {
+        const uint4* kr = reinterpret_cast<const uint4*>(kb + (size_t)key * D);
+        float acc = 0.f;
+#pragma unroll 4
+        for (int c = 0; c < D / 8; ++c) {
+            const uint4 kv4 = kr[c];
+            const uint32_t* k32 = reinterpret_cast<const uint32_t*>(&kv4);
+            const float4 qa = *reinterpret_cast<const float4*>(&sq[c * 8]);
+            const float4 qb = *reinterpret_cast<const float4*>(&sq[c * 8 + 4]);
+            acc += bf16_lo(k32[0]) * qa.x + bf16_hi(k32[0]) * qa.y + bf16_lo(k32[1]) * qa.z + bf16_hi(k32[1]) * qa.w +
+                   bf16_lo(k32[2]) * qb.x + bf16_hi(k32[2]) * qb.y + bf16_lo(k32[3]) * qb.z + bf16_hi(k32[3]) * qb.w;
+        }
+        acc *= scale_log2;
+        sscore[key] = acc;
+        mx = fmaxf(mx, acc);
+    }
+    if (warp == 0) {
+        float acc = 0.f;
+        for (int i = lane; i < D; i += 32) acc += sq[i] * sk[i];
+        acc = warp_sum(acc) * scale_log2;
+        if (lane == 0) sscore[pos] = acc;
+        mx = fmaxf(mx, acc);
+    }
+    mx = warp_max(mx);
+    if (lane == 0) sred[warp] = mx;
+    __syncthreads();
+    if (tid == 0) {
+        float m = sred[0];
+#pragma unroll
+        for (int w = 1; w < FD_THREADS / 32; ++w) m = fmaxf(m, sred[w]);
+        s_bc[0] = m;
+    }
+    __syncthreads();
+    const float m_all = s_bc[0];
+    float lsum = 0.f;
+    for (int key = tid; key <= pos; key += FD_THREADS) {
+        const float p = exp2f(sscore[key] - m_all);
+        lsum += p;
+        sscore[key] = rbf(p);           // P is cast to bf16 before P·V (SDPA contract); l uses the fp32 value
+    }
+    lsum = warp_sum(lsum);
+    __syncthreads();
+    if (lane == 0) sred[warp] = lsum;
+    __syncthreads();
+    // ---- P·V: threads own 8 output dims; key groups stride the cached keys
+    constexpr int TPR = D / 8, KG = FD_THREADS / TPR;
+    const int dd0 = (tid % TPR) * 8, kgi = tid / TPR;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int key = kgi; key < pos; key += KG) {
+        const uint4 vv = *reinterpret_cast<const uint4*>(vb + (size_t)key * D + dd0);
+        const uint32_t* v32 = reinterpret_cast<const uint32_t*>(&vv);
+        const float p = sscore[key];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            acc[2 * j] = fmaf(p, bf16_lo(v32[j]), acc[2 * j]);
+            acc[2 * j + 1] = fmaf(p, bf16_hi(v32[j]), acc[2 * j + 1]);
+        }
+    }
+    if (kgi == 0) {                      // the new token's value
+        const float p = sscore[pos];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(p, sv[dd0 + j], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float v = acc[j];
+#pragma unroll
+        for (int off = TPR; off < 32; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        acc[j] = v;
+    }
+    if (lane < TPR) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) so[warp][dd0 + j] = acc[j];
+    }
+    __syncthreads();
+    if (tid < D) {
+        float l = 0.f, o = 0.f;
+#pragma unroll
+        for (int w = 0; w < FD_THREADS / 32; ++w) { l += sred[w]; o += so[w][tid]; }
+        out[((size_t)b * n_h + h) * D + tid] = f2bf(o / l);
+    }
+}
+
+}  // namespace tl
+
+extern "C" int tl_attn_decode_fused(const void* qkv, void* k_cache, void* v_cache, void* out, const int32_t* pos_dev,
+                                    const void* cos_tab, const void* sin_tab, const void* q_norm_w, const void* k_norm_w,
+                                    float eps, int B, int n_h, int n_kv, int d, int T_max, float scale, void* stream) {
+    using namespace tl;
+    TL_REQUIRE(d == 64 || d == 128, TL_ERR_INVALID, "tl_attn_decode_fused: head_dim %d not in {64,128}", d);
+    TL_REQUIRE(n_kv > 0 && n_h % n_kv == 0, TL_ERR_INVALID, "tl_attn_decode_fused: n_h %% n_kv != 0");
+    TL_REQUIRE(T_max <= FD_MAX_T, TL_ERR_INVALID, "tl_attn_decode_fused: T_max %d > %d (use the split-KV path)", T_max,
+               FD_MAX_T);
+    TL_REQUIRE(pos_dev != nullptr, TL_ERR_INVALID, "tl_attn_decode_fused: pos_dev is null");
+    if (B == 0) return TL_OK;
+    const float sl2 = scale * 1.4426950408889634f;
+    const dim3 grid(n_h, B);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d == 64)
+        attn_decode_fused_kernel<64><<<grid, FD_THREADS, 0, st>>>((const bf16*)qkv, (bf16*)k_cache, (bf16*)v_cache, (bf16*)out,
+                                                                  pos_dev, (const bf16*)cos_tab, (const bf16*)sin_tab,
+                                                                  (const bf16*)q_norm_w, (const bf16*)k_norm_w, eps, n_h, n_kv, T_max, sl2);
+    else
+        attn_decode_fused_kernel<128><<<grid, FD_THREADS, 0, st>>>((const bf16*)qkv, (bf16*)k_cache, (bf16*)v_cache, (bf16*)out,
+                                                                   pos_dev, (const bf16*)cos_tab, (const bf16*)sin_tab,
+                                                                   (const bf16*)q_norm_w, (const bf16*)k_norm_w, eps, n_h, n_kv, T_max, sl2);
+    return check_launch("tl_attn_decode_fused");
+}

@@ -169,17 +169,22 @@ class DistributedModel(torch.nn.Module):
         link, st, cfg = self.link, self.stage, self.cfg
         shape = link.broadcast_object(tuple(input_ids.shape) if link.first else None)
         B, S = shape
-        if link.first:
-            x = st.embed(input_ids.to(self.device))
-        else:
-            x = torch.empty(B, S, cfg.hidden, dtype=torch.bfloat16, device=self.device)
-            link.recv_prev(x)
-        x = st.prefill(x, 0, 0)
-        if not link.last:
-            link.send_next(x.clone())
-            logits = None
-        else:
-            logits = st.head_logits(x.reshape(B * S, cfg.hidden)).view(B, S, cfg.vocab)
+        # micro-batches of at most the stage's per-slot batch flow through the ranks back to back
+        mb = min(B, st.max_batch)
+        parts = []
+        for a in range(0, B, mb):
+            e = min(B, a + mb)
+            if link.first:
+                x = st.embed(input_ids[a:e].to(self.device))
+            else:
+                x = torch.empty(e - a, S, cfg.hidden, dtype=torch.bfloat16, device=self.device)
+                link.recv_prev(x)
+            x = st.prefill(x, 0, 0)
+            if not link.last:
+                link.send_next(x.clone())
+            else:
+                parts.append(st.head_logits(x.reshape((e - a) * S, cfg.hidden)).view(e - a, S, cfg.vocab))
+        logits = torch.cat(parts, dim=0) if parts else None
         if gather and self.world > 1:
             if link.last:
                 link.send_up(logits.contiguous(), 0)

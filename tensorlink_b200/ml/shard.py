@@ -238,14 +238,27 @@ class CudaLayerGroup:
         nat.gemm(w.h, v[f"l{li}.wgu"], out=w.act, flags=nat.EPI_SWIGLU)
         nat.gemm(w.act, v[f"l{li}.wd"], out=x, residual=x)
 
-    def _layer_decode(self, j: int, x: torch.Tensor, B: int, w: ShardBuffers):
-        """Same layer for B <= 8 single-token rows: weight-streaming GEMVs with the norms fused as prologues."""
-        cfg, v, li = self.cfg, self.p.v, self.layer_ids[j]
-        nat.gemv(x, v[f"l{li}.wqkv"], out=w.qkv, bias=v.get(f"l{li}.bqkv"), norm_w=v[f"l{li}.ln1"], eps=cfg.rms_eps)
+    FUSED_DECODE_MAX_T = 2048
+
+    def _decode_attention(self, j: int, li: int, B: int, w: ShardBuffers):
+        """w.qkv (post-bias) -> w.attn for one new token per row.  Short caches: one fused launch (RoPE + append +
+        attention); long caches: RoPE/append, split-KV partials, reduce (three launches, parallel over the KV length)."""
+        cfg, v = self.cfg, self.p.v
+        if self.T_max <= self.FUSED_DECODE_MAX_T and (cfg.n_heads // cfg.n_kv_heads) <= 8:
+            nat.attn_decode_fused(w.qkv, self.kc[j], self.vc[j], w.attn, self.pos_dev, self.cos, self.sin,
+                                  v.get(f"l{li}.qn"), v.get(f"l{li}.kn"), cfg.rms_eps, B, cfg.n_heads, cfg.n_kv_heads,
+                                  cfg.head_dim, self.scale)
+            return
         nat.rope_kv_fwd(w.qkv, w.q, self.kc[j], self.vc[j], self.pos_dev, self.cos, self.sin, v.get(f"l{li}.qn"),
                         v.get(f"l{li}.kn"), cfg.rms_eps, 1, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim)
         nat.attn_decode_fwd(w.q, self.kc[j], self.vc[j], w.attn, self.kvlen_dev, self.dec_ws, B, cfg.n_heads,
                             cfg.n_kv_heads, cfg.head_dim, self.scale)
+
+    def _layer_decode(self, j: int, x: torch.Tensor, B: int, w: ShardBuffers):
+        """Same layer for B <= 8 single-token rows: weight-streaming GEMVs with the norms fused as prologues."""
+        cfg, v, li = self.cfg, self.p.v, self.layer_ids[j]
+        nat.gemv(x, v[f"l{li}.wqkv"], out=w.qkv, bias=v.get(f"l{li}.bqkv"), norm_w=v[f"l{li}.ln1"], eps=cfg.rms_eps)
+        self._decode_attention(j, li, B, w)
         nat.gemv(w.attn, v[f"l{li}.wo"], out=x, residual=x)
         nat.gemv(x, v[f"l{li}.wgu"], out=w.act, norm_w=v[f"l{li}.ln2"], eps=cfg.rms_eps, flags=nat.EPI_SWIGLU)
         nat.gemv(w.act, v[f"l{li}.wd"], out=x, residual=x)
@@ -255,10 +268,7 @@ class CudaLayerGroup:
         cfg, v, li = self.cfg, self.p.v, self.layer_ids[j]
         nat.rmsnorm_fwd(x, v[f"l{li}.ln1"], cfg.rms_eps, out=w.h)
         nat.gemm(w.h, v[f"l{li}.wqkv"], out=w.qkv, bias=v.get(f"l{li}.bqkv"))
-        nat.rope_kv_fwd(w.qkv, w.q, self.kc[j], self.vc[j], self.pos_dev, self.cos, self.sin, v.get(f"l{li}.qn"),
-                        v.get(f"l{li}.kn"), cfg.rms_eps, 1, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim)
-        nat.attn_decode_fwd(w.q, self.kc[j], self.vc[j], w.attn, self.kvlen_dev, self.dec_ws, B, cfg.n_heads,
-                            cfg.n_kv_heads, cfg.head_dim, self.scale)
+        self._decode_attention(j, li, B, w)
         nat.gemm(w.attn, v[f"l{li}.wo"], out=x, residual=x)
         nat.rmsnorm_fwd(x, v[f"l{li}.ln2"], cfg.rms_eps, out=w.h)
         nat.gemm(w.h, v[f"l{li}.wgu"], out=w.act, flags=nat.EPI_SWIGLU)

@@ -113,7 +113,8 @@ class CudaStage:
 
     def n_decode_launches(self, B: int) -> int:
         """Kernel launches inside one decode step of this stage (for bench.py's gpu_launches claim)."""
-        n = len(self.slots[0].layer_ids) * (7 if B <= 8 else 9) + 2
+        fused = self.slots[0].T_max <= self.slots[0].FUSED_DECODE_MAX_T
+        n = len(self.slots[0].layer_ids) * ((7 if B <= 8 else 9) - (2 if fused else 0)) + 2
         if self.has_embed:
             n += 1
         if self.has_head:

@@ -40,6 +40,7 @@ _SIGS = {
     "tl_attn_decode_ws": (c_size_t, [c_int, c_int, c_int, c_int]),
     "tl_attn_decode_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int,
                                    c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "tl_attn_decode_fused": (c_int, [c_void_p] * 9 + [c_float, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "tl_lmhead_ws": (c_size_t, [c_int, c_int]),
     "tl_lmhead_argmax": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_size_t,
                                  c_int, c_int, c_int, c_void_p]),
@@ -339,3 +340,10 @@ def adamw_step(param, grad, m, v, lr, beta1, beta2, eps, wd, step: int, decouple
     require_device()
     _check(load().tl_adamw_step(_p(param), _p(grad), _p(m), _p(v), param.numel(), lr, beta1, beta2, eps, wd, step,
                                 int(decoupled), _stream()), "tl_adamw_step")
+
+
+def attn_decode_fused(qkv, k_cache, v_cache, out, pos_dev, cos_tab, sin_tab, q_norm_w, k_norm_w, eps, B, n_h, n_kv, d, scale):
+    require_device(); _bf16(qkv, k_cache, v_cache, out)
+    _check(load().tl_attn_decode_fused(_p(qkv), _p(k_cache), _p(v_cache), _p(out), _p(pos_dev), _p(cos_tab), _p(sin_tab),
+                                       _p(q_norm_w), _p(k_norm_w), eps, B, n_h, n_kv, d, k_cache.shape[2], scale, _stream()),
+           "tl_attn_decode_fused")

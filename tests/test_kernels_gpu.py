@@ -235,6 +235,39 @@ def test_attn_decode(nat, B, kv_len, n_h, n_kv, d):
     assert O.rel_l2(got, ref) <= TOL_ATTN
 
 
+@pytest.mark.parametrize("cfg", [C.TINY_QWEN2, C.TINY_QWEN2_D128, C.TINY_QWEN3], ids=lambda c: c.name)
+@pytest.mark.parametrize("B,past", [(1, 0), (2, 1), (1, 127), (3, 128), (1, 700)])
+def test_attn_decode_fused_equals_unfused(nat, cfg, B, past):
+    """Fused RoPE + append + attention == rope_kv_fwd -> attn_decode_fwd (same rounding points): outputs within one
+    bf16 ulp-level reordering, cache contents identical; and both satisfy the oracle bound."""
+    d, n_h, n_kv = cfg.head_dim, cfg.n_heads, cfg.n_kv_heads
+    T_max = past + 9
+    qkv = rnd(B, cfg.qkv_dim, seed=70).cuda()
+    qn = dev((1 + 0.1 * torch.randn(d)).bfloat16()) if cfg.qk_norm else None
+    kn = dev((1 + 0.1 * torch.randn(d)).bfloat16()) if cfg.qk_norm else None
+    kc0 = rnd(B, n_kv, T_max, d, seed=71).cuda()
+    vc0 = rnd(B, n_kv, T_max, d, seed=72).cuda()
+    ct, st = nat.rope_table(O.rope_inv_freq(cfg).cuda(), T_max)
+    pos = torch.tensor([past], dtype=torch.int32, device="cuda")
+    kvl = torch.tensor([past + 1], dtype=torch.int32, device="cuda")
+    kc1, vc1 = kc0.clone(), vc0.clone()
+    q = torch.empty(B, cfg.q_dim, dtype=torch.bfloat16, device="cuda")
+    ref = torch.empty(B, cfg.q_dim, dtype=torch.bfloat16, device="cuda")
+    nat.rope_kv_fwd(qkv, q, kc1, vc1, pos, ct, st, qn, kn, cfg.rms_eps, 1, n_h, n_kv, d)
+    ws = torch.empty(nat.attn_decode_ws(B, n_h, d, T_max), dtype=torch.uint8, device="cuda")
+    nat.attn_decode_fwd(q, kc1, vc1, ref, kvl, ws, B, n_h, n_kv, d, d ** -0.5)
+    kc2, vc2 = kc0.clone(), vc0.clone()
+    got = torch.empty_like(ref)
+    nat.attn_decode_fused(qkv, kc2, vc2, got, pos, ct, st, qn, kn, cfg.rms_eps, B, n_h, n_kv, d, d ** -0.5)
+    assert torch.equal(kc1, kc2) and torch.equal(vc1, vc2)
+    assert O.rel_l2(got.cpu(), ref.cpu()) <= 2e-3
+    # oracle: attention of the rotated query over keys 0..past
+    qr = q.cpu().view(B, 1, n_h, d)
+    o_ref = O.attention_sdpa_math(qr.transpose(1, 2), kc1.cpu()[:, :, :past + 1], vc1.cpu()[:, :, :past + 1], d ** -0.5,
+                                  n_h // n_kv)
+    assert O.rel_l2(got.cpu().view(B, 1, -1), o_ref) <= TOL_ATTN
+
+
 @pytest.mark.parametrize("M,V,H", [(1, 1024, 256), (2, 151936, 896), (4, 2048, 512)])
 def test_lmhead_argmax(nat, M, V, H):
     x, w = rnd(M, H, seed=50, std=2.0), rnd(V, H, seed=51, std=0.05)

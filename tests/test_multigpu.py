@@ -22,7 +22,8 @@ def test_two_gpu_pipeline_equals_single_stage(tmp_path):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "multigpu_worker.py"), str(tmp_path)]
     r = subprocess.run(cmd, env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stderr[-4000:]
+    errs = "".join(open(p).read() for p in sorted(map(str, tmp_path.glob("err*.txt"))))
+    assert r.returncode == 0, errs or r.stderr[-4000:]
     r0, r1 = torch.load(tmp_path / "rank0.pt"), torch.load(tmp_path / "rank1.pt")
     assert r0["logits_equal"] and r0["gen_equal"]
     assert r0["gen_graph_vs_eager"] and r1["gen_graph_vs_eager"]

@@ -21,7 +21,8 @@ def test_two_rank_pipeline(tmp_path):
            "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "pipeline_worker.py"), str(tmp_path)]
     env = dict(os.environ, OMP_NUM_THREADS="2", PYTHONPATH=ROOT)
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stderr[-3000:]
+    errs = "".join(open(p).read() for p in sorted(map(str, tmp_path.glob("err*.txt"))))
+    assert r.returncode == 0, errs or r.stderr[-3000:]
     r0, r1 = torch.load(tmp_path / "rank0.pt"), torch.load(tmp_path / "rank1.pt")
     assert r0["logits_equal"]
     assert r0["gen_equal"] and r1["gen_equal"] and r0["gen2_equal"] and r1["gen2_equal"]
