@@ -181,6 +181,80 @@ def measure_gemv_launches(dm, rows):
     return out
 
 
+def measure_training(args, N, rank, world, tf_peak, peak_kind):
+    """Secondary metric (BASELINE config 2 shape): one optimizer step = forward + backward + Adam through
+    ``DistributedModel`` / ``create_optimizer`` with ids and labels copied from pinned host memory each step."""
+    import torch
+    import torch.distributed as dist
+    from tensorlink_b200 import native as nat
+    from tensorlink_b200.ml import DistributedModel
+    from tensorlink_b200.ml.configs import get_config
+    from tensorlink_b200.ml.weights import synthetic_tokens
+    cfg = get_config(args.train_model)
+    B, S = args.train_batch * N, args.train_seq
+    dm = DistributedModel(args.train_model, training=True, n_pipelines=N, max_batch=B, max_seq=S, init="device",
+                          optimizer=torch.optim.Adam, max_tokens=8)
+    opt = dm.create_optimizer(lr=1e-4)
+    ids_host = synthetic_tokens(cfg, B, S).pin_memory()
+
+    def step():
+        ids = ids_host.to(dm.device, non_blocking=True) if rank == 0 else None
+        opt.zero_grad()
+        out = dm(ids, labels=ids)
+        out.loss.backward()
+        opt.step()
+        return out.loss
+
+    for _ in range(3):
+        loss = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tr = dm.stage.trainer
+    l0 = tr.launches
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dm.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t = float(t)
+    tokens = B * S
+    flops = 6 * cfg.n_layers * cfg.layer_matmul_params() * tokens + 6 * cfg.vocab * cfg.hidden * tokens \
+        + 3 * cfg.n_layers * 2 * B * S * S * cfg.n_heads * cfg.head_dim
+    # dominant kernel live: the gate/up forward GEMM of one layer
+    M, Nn, K = (B // N) * S, 2 * cfg.intermediate, cfg.hidden
+    a = torch.randn(M, K, device=dm.device).bfloat16()
+    w = dm.stage.params.v[f"l{dm.stage.params.layer_ids[0]}.wgu"]
+    o = torch.empty(M, Nn, dtype=torch.bfloat16, device=dm.device)
+    for _ in range(3):
+        nat.gemm(a, w, out=o)
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(10):
+        nat.gemm(a, w, out=o)
+    g1.record()
+    torch.cuda.synchronize()
+    tg = g0.elapsed_time(g1) * 1e-4
+    ach = 2.0 * M * Nn * K / tg / 1e12
+    res = {"metric": "training samples/sec", "value": B * args.steps / t, "unit": "samples/s", "ms_per_step": t / args.steps * 1e3,
+           "loss": float(loss), "config": {"workload": f"{args.train_model} bf16, one optimizer step (fwd + bwd + Adam), "
+                                                       f"global batch {B} x seq {S}, {N} micro-batch(es), {N} stage(s)",
+                                           "h2d_bytes_per_step": B * S * 8, "d2h_bytes_per_step": 4},
+           "model_tflops_per_s": flops * args.steps / t / 1e12, "gpu_launches": tr.launches - l0,
+           "roofline": {"bound": "tensor", "kernel": "tl::gemm_bf16_kernel (gate/up forward GEMM)", "achieved": ach,
+                        "peak": tf_peak, "peak_kind": f"{peak_kind} cuBLAS bf16 (sustained)", "unit": "TFLOP/s", "frac": ach / tf_peak,
+                        "traffic": None, "algorithmic_flops_per_launch": 2.0 * M * Nn * K, "launch_s": tg}}
+    del dm, opt
+    torch.cuda.empty_cache()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -190,6 +264,10 @@ def main():
     ap.add_argument("--rows-per-gpu", type=int, default=1)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step measurement")
+    ap.add_argument("--train-model", default="Qwen/Qwen2.5-0.5B")
+    ap.add_argument("--train-batch", type=int, default=8)
+    ap.add_argument("--train-seq", type=int, default=512)
     args = ap.parse_args()
     name, prompt, new = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -307,6 +385,10 @@ def main():
                 e2e={"value": toks / t_e2e, "unit": "tokens/s", "h2d_bytes_per_step": rows * prompt * 8,
                      "d2h_bytes_per_step": rows * (prompt + new) * 8},
                 gpu_launches=launches, clocks=clocks, roofline=roof)
+    if not args.no_train:
+        del dm
+        torch.cuda.empty_cache()
+        line["train"] = measure_training(args, N, rank, world, tf_peak, peak_kind)
     if rank == 0:
         if N == 1 and not args.no_cpu_baseline:
             ref = CpuReference(cfg, rows, prompt, budget_layers=1 if cfg.hidden > 2048 else 2)
