@@ -243,7 +243,7 @@ def measure_training(args, N, rank, world, tf_peak, peak_kind):
     tg = g0.elapsed_time(g1) * 1e-4
     ach = 2.0 * M * Nn * K / tg / 1e12
     res = {"metric": "training samples/sec", "value": B * args.steps / t, "unit": "samples/s", "ms_per_step": t / args.steps * 1e3,
-           "loss": float(loss), "config": {"workload": f"{args.train_model} bf16, one optimizer step (fwd + bwd + Adam), "
+           "loss": float(loss.detach()), "config": {"workload": f"{args.train_model} bf16, one optimizer step (fwd + bwd + Adam), "
                                                        f"global batch {B} x seq {S}, {N} micro-batch(es), {N} stage(s)",
                                            "h2d_bytes_per_step": B * S * 8, "d2h_bytes_per_step": 4},
            "model_tflops_per_s": flops * args.steps / t / 1e12, "gpu_launches": tr.launches - l0,

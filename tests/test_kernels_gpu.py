@@ -260,7 +260,7 @@ def test_attn_decode_fused_equals_unfused(nat, cfg, B, past):
     got = torch.empty_like(ref)
     nat.attn_decode_fused(qkv, kc2, vc2, got, pos, ct, st, qn, kn, cfg.rms_eps, B, n_h, n_kv, d, d ** -0.5)
     assert torch.equal(kc1, kc2) and torch.equal(vc1, vc2)
-    assert O.rel_l2(got.cpu(), ref.cpu()) <= 2e-3
+    assert O.rel_l2(got.cpu(), ref.cpu()) <= TOL_ATTN      # two valid P-rounding orders (global vs per-split max)
     # oracle: attention of the rotated query over keys 0..past
     qr = q.cpu().view(B, 1, n_h, d)
     o_ref = O.attention_sdpa_math(qr.transpose(1, 2), kc1.cpu()[:, :, :past + 1], vc1.cpu()[:, :, :past + 1], d ** -0.5,
