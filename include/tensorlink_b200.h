@@ -117,6 +117,39 @@ int tl_advance_pos(int32_t* pos_dev, int32_t* kv_len_dev, int delta, void* strea
  * (replaces the per-token TOKEN packet, tensorlink/p2p/torch_node.py:543-551) */
 int tl_append_token(const int64_t* ids, int64_t* out_tokens, int32_t* step_dev, int B, int ld, void* stream);
 
+/* ---- one decode step of a pipeline stage as ONE persistent kernel (csrc/decode_step.cu) -------------------
+ * The job list replaces the per-layer launch sequence of `DistributedWorker._handle_forward` ->
+ * `module(**kwargs)` (tensorlink/ml/worker.py:297-357) for single-token rows: the weight stream of job j+1
+ * is prefetched while job j finishes, grid barriers publish each job's output vector. */
+#define TL_JOB_GEMV 0     /* y[M,N or N/2] = f(norm(x)[M,K] W[N,K]^T): same semantics and flags as tl_gemv_bf16 */
+#define TL_JOB_ATTN 1     /* RoPE + KV append + attention: same semantics as tl_attn_decode_fused (x = qkv, y = out) */
+#define TL_JOB_EMBED 2    /* y[m,:] = W[ids[m],:]: x = int64 ids, W = table[N=vocab, K=hidden] */
+#define TL_JOB_ARGMAX 3   /* y = int64 ids[M] = argmax over x = bf16 logits[M,N]; W = workspace (>= M*grid*8 bytes) */
+#define TL_JOB_ADVANCE 4  /* *pos_dev += 1; if y != NULL *(int32*)y = new pos */
+typedef struct tl_decode_job {
+    int32_t type, N, K, flags;
+    int32_t n_h, n_kv, d, T_max;
+    float eps, scale;
+    const void* W;
+    const void* x;
+    void* y;
+    const void* bias;
+    const void* residual;
+    const void* norm_w;
+    const void* pos_dev;
+    const void* cos_tab;
+    const void* sin_tab;
+    const void* q_norm_w;
+    const void* k_norm_w;
+    void* k_cache;
+    void* v_cache;
+} tl_decode_job;
+/* sync_ws: >= tl_decode_step_ws(M) bytes, zero-initialised once (the kernel leaves it zeroed).  jobs_host is the
+ * host copy of the same list (shape validation and shared-memory sizing); M <= 4 rows. */
+size_t tl_decode_step_ws(int M);
+int tl_decode_step(const tl_decode_job* jobs_dev, const tl_decode_job* jobs_host, int n_jobs, int M, void* sync_ws,
+                   void* stream);
+
 /* ---- training-only pieces (K8/K9/K10): replace the autograd graph of `assoc_output.backward(loss)`
  * (tensorlink/ml/worker.py:271) and `optimizer.step()` (tensorlink/ml/worker.py:1317) ------------------------- */
 /* SwiGLU on interleaved gate/up pre-activations gu[M,2I] (col 2j = gate_j, 2j+1 = up_j): h[M,I], HF rounding */

@@ -199,18 +199,26 @@ class CudaLayerGroup:
         self.kvlen_dev = torch.zeros(1, dtype=torch.int32, device=dev)    # valid keys for the decode kernel
         self.n_max = max_tokens or max_batch * max_seq
         self._alloc_bufs(min(self.n_max, 8))
+        self.dbufs = self._make_bufs(max_batch)       # decode-time buffers: fixed addresses (captured graphs, job lists)
         self.dec_ws = torch.empty(max(nat.attn_decode_ws(max_batch, cfg.n_heads, cfg.head_dim, max_seq), 16),
                                   dtype=torch.uint8, device=dev)
         self.scale = cfg.head_dim ** -0.5
 
-    def _alloc_bufs(self, n: int):
+    def _make_bufs(self, n: int) -> ShardBuffers:
         cfg, dev, bf = self.cfg, self.device, torch.bfloat16
-        self.bufs = ShardBuffers(
+        return ShardBuffers(
             x=torch.empty(n, cfg.hidden, dtype=bf, device=dev), h=torch.empty(n, cfg.hidden, dtype=bf, device=dev),
             qkv=torch.empty(n, cfg.qkv_dim, dtype=bf, device=dev), q=torch.empty(n, cfg.q_dim, dtype=bf, device=dev),
             attn=torch.empty(n, cfg.q_dim, dtype=bf, device=dev),
             act=torch.empty(n, cfg.intermediate, dtype=bf, device=dev))
+
+    def _alloc_bufs(self, n: int):
+        self.bufs = self._make_bufs(n)
         self.n_alloc = n
+
+    def _dbufs(self, n: int) -> ShardBuffers:
+        b = self.dbufs
+        return ShardBuffers(b.x[:n], b.h[:n], b.qkv[:n], b.q[:n], b.attn[:n], b.act[:n])
 
     def _bufs(self, n: int) -> ShardBuffers:
         if n > self.n_alloc:
@@ -295,7 +303,7 @@ class CudaLayerGroup:
         Graph-capturable: the write position and the KV length live in device memory and are advanced by
         kernels inside the same launch sequence (kv_len += 1 before the layers, pos += 1 after)."""
         B = x.shape[0]
-        w = self._bufs(B)
+        w = self._dbufs(B)
         nat.advance_pos(self.kvlen_dev, None, 1)
         for j in range(self.num_layers):
             if B <= 8:
@@ -303,6 +311,28 @@ class CudaLayerGroup:
             else:
                 self._layer_decode_batched(j, x, B, w)
         nat.advance_pos(self.pos_dev, None, 1)
+
+    def decode_jobs(self, x: torch.Tensor, B: int) -> list:
+        """The layer part of a decode step as ``tl_decode_job`` entries (x [B,H] updated in place)."""
+        cfg, v = self.cfg, self.p.v
+        w = self._dbufs(B)
+        J = nat.DecodeJobList.job
+        jobs = []
+        for j, li in enumerate(self.layer_ids):
+            bq = v.get(f"l{li}.bqkv")
+            jobs.append(J(nat.JOB_GEMV, N=cfg.qkv_dim, K=cfg.hidden, flags=nat.EPI_BIAS if bq is not None else 0, W=v[f"l{li}.wqkv"],
+                          x=x, y=w.qkv, bias=bq, norm_w=v[f"l{li}.ln1"], eps=cfg.rms_eps))
+            jobs.append(J(nat.JOB_ATTN, x=w.qkv, y=w.attn, k_cache=self.kc[j], v_cache=self.vc[j], pos_dev=self.pos_dev,
+                          cos_tab=self.cos, sin_tab=self.sin, q_norm_w=v.get(f"l{li}.qn"), k_norm_w=v.get(f"l{li}.kn"),
+                          n_h=cfg.n_heads, n_kv=cfg.n_kv_heads, d=cfg.head_dim, T_max=self.T_max, scale=self.scale,
+                          eps=cfg.rms_eps))
+            jobs.append(J(nat.JOB_GEMV, N=cfg.hidden, K=cfg.q_dim, flags=nat.EPI_RESIDUAL, W=v[f"l{li}.wo"], x=w.attn, y=x,
+                          residual=x))
+            jobs.append(J(nat.JOB_GEMV, N=2 * cfg.intermediate, K=cfg.hidden, flags=nat.EPI_SWIGLU, W=v[f"l{li}.wgu"], x=x,
+                          y=w.act, norm_w=v[f"l{li}.ln2"], eps=cfg.rms_eps))
+            jobs.append(J(nat.JOB_GEMV, N=cfg.hidden, K=cfg.intermediate, flags=nat.EPI_RESIDUAL, W=v[f"l{li}.wd"], x=w.act,
+                          y=x, residual=x))
+        return jobs
 
     # ------------------------------------------------------------------------------------------ reference-shaped API
     def forward(self, **kwargs) -> dict:

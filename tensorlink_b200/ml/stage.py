@@ -41,6 +41,8 @@ class CudaStage:
         self.x_dec = [torch.zeros(max_batch, cfg.hidden, dtype=torch.bfloat16, device=dev) for _ in range(n_slots)]
         self.ids_dec = [torch.zeros(max_batch, dtype=torch.int64, device=dev) for _ in range(n_slots)]
         self.graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
+        self.job_lists: Dict[tuple, object] = {}
+        self.step_ws = torch.zeros(nat.decode_step_ws(4), dtype=torch.uint8, device=dev)
         if has_head:
             self.head_ws = torch.empty(max(nat.lmhead_ws(min(max_batch, 8), cfg.vocab), max_batch * 64 * 8 + 256),
                                        dtype=torch.uint8, device=dev)
@@ -76,7 +78,37 @@ class CudaStage:
             nat.argmax_bf16(self.logits_dec[:B], ids_out, self.head_ws)
 
     # ------------------------------------------------------------------------------------------ decode step
+    def _use_step_kernel(self, B: int) -> bool:
+        """One persistent kernel per decode step (csrc/decode_step.cu) when the shapes allow it;
+        TL_DECODE_IMPL=kernels forces the per-kernel launch sequence (A/B tests)."""
+        import os
+        g = self.slots[0]
+        return (os.environ.get("TL_DECODE_IMPL", "step") != "kernels" and B <= 4 and g.T_max <= g.FUSED_DECODE_MAX_T
+                and self.cfg.n_heads * B <= 148 and self.cfg.n_heads // self.cfg.n_kv_heads <= 8)
+
+    def _step_jobs(self, slot: int, B: int):
+        key = (slot, B)
+        if key not in self.job_lists:
+            cfg, v, grp = self.cfg, self.params.v, self.slots[slot]
+            J = nat.DecodeJobList.job
+            x = self.x_dec[slot][:B]
+            jobs = []
+            if self.has_embed:
+                jobs.append(J(nat.JOB_EMBED, N=cfg.vocab, K=cfg.hidden, W=v["embed"], x=self.ids_dec[slot], y=x))
+            jobs += grp.decode_jobs(x, B)
+            if self.has_head:
+                jobs.append(J(nat.JOB_GEMV, N=cfg.vocab, K=cfg.hidden, flags=0, W=v["head"], x=x, y=self.logits_dec,
+                              norm_w=v["norm"], eps=cfg.rms_eps))
+                jobs.append(J(nat.JOB_ARGMAX, N=cfg.vocab, x=self.logits_dec, y=self.ids_dec[slot],
+                              W=self.step_ws.data_ptr() + 64))
+            jobs.append(J(nat.JOB_ADVANCE, pos_dev=grp.pos_dev, y=grp.kvlen_dev))
+            self.job_lists[key] = nat.DecodeJobList(jobs, self.device)
+        return self.job_lists[key]
+
     def _decode_body(self, slot: int, B: int):
+        if self._use_step_kernel(B):
+            nat.decode_step(self._step_jobs(slot, B), B, self.step_ws)
+            return
         x = self.x_dec[slot][:B]
         if self.has_embed:
             nat.embed_fwd(self.ids_dec[slot][:B], self.params.v["embed"], out=x)
@@ -113,6 +145,8 @@ class CudaStage:
 
     def n_decode_launches(self, B: int) -> int:
         """Kernel launches inside one decode step of this stage (for bench.py's gpu_launches claim)."""
+        if self._use_step_kernel(B):
+            return 1
         fused = self.slots[0].T_max <= self.slots[0].FUSED_DECODE_MAX_T
         n = len(self.slots[0].layer_ids) * ((7 if B <= 8 else 9) - (2 if fused else 0)) + 2
         if self.has_embed:

@@ -41,6 +41,8 @@ _SIGS = {
     "tl_attn_decode_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int,
                                    c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "tl_attn_decode_fused": (c_int, [c_void_p] * 9 + [c_float, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "tl_decode_step_ws": (c_size_t, [c_int]),
+    "tl_decode_step": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "tl_lmhead_ws": (c_size_t, [c_int, c_int]),
     "tl_lmhead_argmax": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_size_t,
                                  c_int, c_int, c_int, c_void_p]),
@@ -63,6 +65,20 @@ _SIGS = {
     "tl_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float, c_float, c_float,
                               c_float, c_int, c_int, c_void_p]),
 }
+
+
+
+class DecodeJob(ctypes.Structure):
+    """``tl_decode_job`` (include/tensorlink_b200.h)."""
+    _fields_ = [("type", c_int32), ("N", c_int32), ("K", c_int32), ("flags", c_int32),
+                ("n_h", c_int32), ("n_kv", c_int32), ("d", c_int32), ("T_max", c_int32),
+                ("eps", c_float), ("scale", c_float),
+                ("W", c_void_p), ("x", c_void_p), ("y", c_void_p), ("bias", c_void_p), ("residual", c_void_p),
+                ("norm_w", c_void_p), ("pos_dev", c_void_p), ("cos_tab", c_void_p), ("sin_tab", c_void_p),
+                ("q_norm_w", c_void_p), ("k_norm_w", c_void_p), ("k_cache", c_void_p), ("v_cache", c_void_p)]
+
+
+JOB_GEMV, JOB_ATTN, JOB_EMBED, JOB_ARGMAX, JOB_ADVANCE = 0, 1, 2, 3, 4
 
 _lib: Optional[ctypes.CDLL] = None
 
@@ -347,3 +363,33 @@ def attn_decode_fused(qkv, k_cache, v_cache, out, pos_dev, cos_tab, sin_tab, q_n
     _check(load().tl_attn_decode_fused(_p(qkv), _p(k_cache), _p(v_cache), _p(out), _p(pos_dev), _p(cos_tab), _p(sin_tab),
                                        _p(q_norm_w), _p(k_norm_w), eps, B, n_h, n_kv, d, k_cache.shape[2], scale, _stream()),
            "tl_attn_decode_fused")
+
+
+def decode_step_ws(M: int) -> int:
+    return int(load().tl_decode_step_ws(M))
+
+
+class DecodeJobList:
+    """Host + device copies of a ``tl_decode_job`` array (device copy owned by a torch uint8 tensor)."""
+
+    def __init__(self, jobs, device):
+        self.n = len(jobs)
+        self.host = (DecodeJob * self.n)(*jobs)
+        raw = bytes(self.host)
+        self.dev = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+
+    @staticmethod
+    def job(type_, **kw) -> DecodeJob:
+        j = DecodeJob()
+        j.type = type_
+        for k, v in kw.items():
+            if isinstance(v, torch.Tensor):
+                v = v.data_ptr()
+            setattr(j, k, v)
+        return j
+
+
+def decode_step(jobs: DecodeJobList, M: int, sync_ws: torch.Tensor):
+    require_device()
+    _check(load().tl_decode_step(_p(jobs.dev), ctypes.cast(jobs.host, c_void_p), jobs.n, M, _p(sync_ws), _stream()),
+           "tl_decode_step")
