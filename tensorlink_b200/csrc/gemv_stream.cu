@@ -9,6 +9,8 @@
 // product finishes with one warp reduction and no cross-warp traffic.  x (optionally RMS-normalised with HF
 // rounding) is staged once per CTA while the producer is already streaming.
 // Algorithmic bytes per launch = 2*N*K.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace tl {
@@ -27,14 +29,16 @@ template <int M>
 __global__ void __launch_bounds__(GS_THREADS, 1)
 gemv_stream_kernel(const bf16* __restrict__ x, const bf16* __restrict__ W, bf16* __restrict__ y, int N, int K,
                    const bf16* __restrict__ bias, const bf16* __restrict__ residual, const bf16* __restrict__ norm_w,
-                   float eps, int flags, int P, int n_stages, int NW) {
+                   float eps, int flags, int P, int n_stages, int NW, int stage_bytes) {
     extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char* ring = smem;                                                    // [n_stages][GS_STAGE_BYTES]
-    bf16* xs = reinterpret_cast<bf16*>(smem + (size_t)n_stages * GS_STAGE_BYTES);  // [M][K]
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)n_stages * GS_STAGE_BYTES + (((size_t)M * K * 2 + 15) & ~(size_t)15));
+    unsigned char* ring = smem;                                                    // [n_stages][stage_bytes]
+    bf16* xs = reinterpret_cast<bf16*>(smem + (size_t)n_stages * stage_bytes);     // [M][K]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)n_stages * stage_bytes + (((size_t)M * K * 2 + 15) & ~(size_t)15));
     uint64_t* empty_bar = full_bar + GS_MAX_STAGES;
     __shared__ float s_part[GS_CONSUMER_WARPS][M];
 
+    // programmatic dependent launch: let the next kernel's CTAs start (and prefetch ITS weights) as SMs free up
+    asm volatile("griddepcontrol.launch_dependents;");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int npairs = N >> 1;
     const int p_begin = (int)((long long)blockIdx.x * npairs / gridDim.x);
@@ -66,7 +70,7 @@ gemv_stream_kernel(const bf16* __restrict__ x, const bf16* __restrict__ W, bf16*
                     for (int w = 0; w < NW; ++w) {
                         const int unit = g * NW + w;
                         mbar_wait(&empty_bar[stage], phase ^ 1);
-                        unsigned char* dst = ring + (size_t)stage * GS_STAGE_BYTES;
+                        unsigned char* dst = ring + (size_t)stage * stage_bytes;
                         if (unit >= n_units) {
                             mbar_expect_tx(&full_bar[stage], 0);
                         } else {
@@ -91,6 +95,9 @@ gemv_stream_kernel(const bf16* __restrict__ x, const bf16* __restrict__ W, bf16*
         }
     } else {
         // ================================================================= consumers
+        // x / residual are produced by the previous kernel: wait for it (no-op without the PDL launch attribute);
+        // the producer warp above streams weights, which nobody writes, without waiting.
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         const int nvec = K >> 3;
         if (norm_w) {
             float ss[M];
@@ -205,7 +212,7 @@ gemv_stream_kernel(const bf16* __restrict__ x, const bf16* __restrict__ W, bf16*
                 const int stage = seq % n_stages;
                 const uint32_t phase = (uint32_t)(seq / n_stages) & 1u;
                 mbar_wait(&full_bar[stage], phase);
-                const unsigned char* src = ring + (size_t)stage * GS_STAGE_BYTES;
+                const unsigned char* src = ring + (size_t)stage * stage_bytes;
                 if (valid) {
                     if (!chunked) {
                         const int np = min(P, p_end - pair0);
@@ -250,25 +257,42 @@ static int launch_stream(const void* x, const void* W, void* y, int N, int K, co
     }
     const size_t xs_bytes = (((size_t)M * K * 2) + 15) & ~(size_t)15;
     const size_t fixed = xs_bytes + 2 * GS_MAX_STAGES * sizeof(uint64_t);
-    int max_stages = (int)((SMEM_CAP - fixed) / GS_STAGE_BYTES);
+    const bool chunked = K > GS_KC || (size_t)K * 4 > GS_STAGE_BYTES;
+    int P = chunked ? 1 : (int)(GS_STAGE_BYTES / ((size_t)K * 4));
+    if (P < 1) P = 1;
+    if (P > 8) P = 8;
+    // a stage holds exactly one unit: P whole pairs, or one 4096-column chunk of one pair
+    const int stage_bytes = chunked ? GS_STAGE_BYTES : (int)((((size_t)P * K * 4) + 127) & ~(size_t)127);
+    int max_stages = (int)((SMEM_CAP - fixed) / stage_bytes);
     if (max_stages > GS_MAX_STAGES) max_stages = GS_MAX_STAGES;
     if (max_stages < 4) return 1;   // caller falls back to the register-streaming kernel
     // pick (n_stages, NW): n_stages a multiple of NW, as many bytes in flight as possible, then as many warps
     int n_stages = 0, NW = 0;
     for (int nw = GS_CONSUMER_WARPS; nw >= 4; --nw) {
-        const int st = max_stages / nw * nw;
-        if (st > n_stages) { n_stages = st; NW = nw; }
+        const int st_ = max_stages / nw * nw;
+        if (st_ > n_stages) { n_stages = st_; NW = nw; }
     }
-    const size_t smem = (size_t)n_stages * GS_STAGE_BYTES + fixed;
-    const bool chunked = K > GS_KC || (size_t)K * 4 > GS_STAGE_BYTES;
-    int P = chunked ? 1 : (int)(GS_STAGE_BYTES / ((size_t)K * 4));
-    if (P < 1) P = 1;
-    if (P > 8) P = 8;
+    const size_t smem = (size_t)n_stages * stage_bytes + fixed;
     const int npairs = N >> 1;
     int grid = sm_count();
     if (grid > npairs) grid = npairs;
-    kern<<<grid, GS_THREADS, smem, st>>>((const bf16*)x, (const bf16*)W, (bf16*)y, N, K, (const bf16*)bias,
-                                         (const bf16*)residual, (const bf16*)norm_w, eps, flags, P, n_stages, NW);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(GS_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static int use_pdl = -1;
+    if (use_pdl < 0) {
+        const char* e = getenv("TL_PDL");
+        use_pdl = (e && e[0] == '0') ? 0 : 1;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = use_pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, (const bf16*)x, (const bf16*)W, (bf16*)y, N, K, (const bf16*)bias, (const bf16*)residual,
+                       (const bf16*)norm_w, eps, flags, P, n_stages, NW, stage_bytes);
     return check_launch("tl_gemv_bf16/stream");
 }
 

@@ -79,11 +79,12 @@ class CudaStage:
 
     # ------------------------------------------------------------------------------------------ decode step
     def _use_step_kernel(self, B: int) -> bool:
-        """One persistent kernel per decode step (csrc/decode_step.cu) when the shapes allow it;
-        TL_DECODE_IMPL=kernels forces the per-kernel launch sequence (A/B tests)."""
+        """TL_DECODE_IMPL=step selects ONE persistent kernel per decode step (csrc/decode_step.cu: bit-identical,
+        measured 321 vs 343 tok/s at Qwen2.5-7B B=1 in round 1, so the per-kernel sequence under a CUDA graph with
+        programmatic dependent launches stays the default)."""
         import os
         g = self.slots[0]
-        return (os.environ.get("TL_DECODE_IMPL", "step") != "kernels" and B <= 4 and g.T_max <= g.FUSED_DECODE_MAX_T
+        return (os.environ.get("TL_DECODE_IMPL", "kernels") == "step" and B <= 4 and g.T_max <= g.FUSED_DECODE_MAX_T
                 and self.cfg.n_heads * B <= 148 and self.cfg.n_heads // self.cfg.n_kv_heads <= 8)
 
     def _step_jobs(self, slot: int, B: int):

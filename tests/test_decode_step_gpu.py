@@ -45,10 +45,14 @@ def test_step_kernel_full_size_05b():
 def test_step_kernel_repeated_launches_leave_sync_clean():
     from tensorlink_b200.ml import DistributedModel
     cfg = C.TINY_QWEN2_D128
-    dm = DistributedModel(cfg, training=False, max_batch=2, max_seq=64)
-    ids = synthetic_tokens(cfg, 2, 9)
-    x = dm.generate(ids, max_new_tokens=30).cpu()
-    y = dm.generate(ids, max_new_tokens=30).cpu()
-    z = dm.generate(ids, max_new_tokens=30, use_graph=False).cpu()
+    os.environ["TL_DECODE_IMPL"] = "step"
+    try:
+        dm = DistributedModel(cfg, training=False, max_batch=2, max_seq=64)
+        ids = synthetic_tokens(cfg, 2, 9)
+        x = dm.generate(ids, max_new_tokens=30).cpu()
+        y = dm.generate(ids, max_new_tokens=30).cpu()
+        z = dm.generate(ids, max_new_tokens=30, use_graph=False).cpu()
+    finally:
+        os.environ.pop("TL_DECODE_IMPL", None)
     assert torch.equal(x, y) and torch.equal(x, z)
     assert int(dm.stage.step_ws[:8].view(torch.int32).abs().sum()) == 0
