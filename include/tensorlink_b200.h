@@ -162,6 +162,10 @@ int tl_rmsnorm_bwd(const void* x, const void* w, const void* dy, const float* rs
 /* RoPE backward + KV gather: dqkv[n, (n_h+2n_kv)*d] from dq[n, n_h*d] and dk/dv[B, n_kv, T_max, d] */
 int tl_rope_kv_bwd(const void* dq, const void* dk, const void* dv, void* dqkv, const void* cos_tab,
                    const void* sin_tab, int n_tokens, int S, int n_h, int n_kv, int d, int T_max, void* stream);
+/* Qwen3 q/k-norm backward, in place on the q and k slices of dqkv[n, (n_h+2n_kv)*d] (gradient w.r.t. the
+ * normalised vectors on entry, w.r.t. the pre-norm vectors on exit); gain gradients accumulate in fp32 [d] */
+int tl_qk_norm_bwd(const void* qkv_pre, void* dqkv, const void* q_norm_w, const void* k_norm_w, float* dqn_accum,
+                   float* dkn_accum, float eps, int n_tokens, int n_h, int n_kv, int d, void* stream);
 /* attention backward (recompute P from lse): dq[B,S,n_h,d]; dk/dv[B,n_kv,T_max,d] rows < S */
 size_t tl_attn_bwd_ws(int B, int S, int n_h);
 int tl_attn_bwd(const void* q, const void* k_cache, const void* v_cache, const void* out, const void* dout,

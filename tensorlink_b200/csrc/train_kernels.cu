@@ -153,6 +153,50 @@ __global__ void __launch_bounds__(128) rope_kv_bwd_kernel(const bf16* __restrict
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------ q/k-norm backward
+// Qwen3: q and k heads are RMS-normalised over the head dim before RoPE (modeling_qwen3.py:248-264).  One warp per
+// (token, q-or-k head): recompute rstd from the saved pre-norm qkv, replace the gradient slice of dqkv in place by
+// the gradient w.r.t. the pre-norm vector, accumulate the gain gradients in fp32.
+template <int D>
+__global__ void __launch_bounds__(128) qk_norm_bwd_kernel(const bf16* __restrict__ qkv_pre, bf16* __restrict__ dqkv,
+                                                           const bf16* __restrict__ qn, const bf16* __restrict__ kn,
+                                                           float* __restrict__ dqn, float* __restrict__ dkn, float eps,
+                                                           int n_tokens, int n_h, int n_kv) {
+    constexpr int PER = D / 32;
+    const int heads = n_h + 2 * n_kv, nh_qk = n_h + n_kv;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (gw >= n_tokens * nh_qk) return;
+    const int n = gw / nh_qk, h = gw - n * nh_qk;
+    const bool is_q = h < n_h;
+    const size_t off = (size_t)n * heads * D + (size_t)h * D;
+    const bf16* w = is_q ? qn : kn;
+    float x[PER], g[PER], dy[PER];
+    float ss = 0.f;
+#pragma unroll
+    for (int p = 0; p < PER; ++p) {
+        x[p] = bf2f(qkv_pre[off + lane + 32 * p]);
+        ss += x[p] * x[p];
+    }
+    ss = warp_sum(ss);
+    const float rstd = 1.0f / sqrtf(ss / (float)D + eps);
+    float dot = 0.f;
+#pragma unroll
+    for (int p = 0; p < PER; ++p) {
+        dy[p] = bf2f(dqkv[off + lane + 32 * p]);
+        g[p] = dy[p] * bf2f(w[lane + 32 * p]);
+        dot += g[p] * x[p] * rstd;
+    }
+    dot = warp_sum(dot) / (float)D;
+    float* dw = is_q ? dqn : dkn;
+#pragma unroll
+    for (int p = 0; p < PER; ++p) {
+        const float nrm = x[p] * rstd;
+        dqkv[off + lane + 32 * p] = f2bf(rstd * (g[p] - nrm * dot));
+        atomicAdd(&dw[lane + 32 * p], dy[p] * rbf(nrm));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ cross entropy
 // one CTA per row: loss_sum += logsumexp(row) - row[label]; dlogits = (softmax - onehot) * grad_scale (in place ok)
 constexpr int CE_THREADS = 512;
@@ -358,6 +402,23 @@ int tl_rope_kv_bwd(const void* dq, const void* dk, const void* dv, void* dqkv, c
         rope_kv_bwd_kernel<128><<<grid, 128, 0, st>>>((const bf16*)dq, (const bf16*)dk, (const bf16*)dv, (bf16*)dqkv,
                                                       (const bf16*)cos_tab, (const bf16*)sin_tab, n_tokens, S, n_h, n_kv, T_max);
     return check_launch("tl_rope_kv_bwd");
+}
+
+int tl_qk_norm_bwd(const void* qkv_pre, void* dqkv, const void* q_norm_w, const void* k_norm_w, float* dqn_accum,
+                   float* dkn_accum, float eps, int n_tokens, int n_h, int n_kv, int d, void* stream) {
+    using namespace tl;
+    TL_REQUIRE(d == 64 || d == 128, TL_ERR_INVALID, "tl_qk_norm_bwd: head_dim %d not in {64,128}", d);
+    if (n_tokens == 0) return TL_OK;
+    const long long warps = (long long)n_tokens * (n_h + n_kv);
+    const int grid = (int)((warps + 3) / 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d == 64)
+        qk_norm_bwd_kernel<64><<<grid, 128, 0, st>>>((const bf16*)qkv_pre, (bf16*)dqkv, (const bf16*)q_norm_w, (const bf16*)k_norm_w,
+                                                     dqn_accum, dkn_accum, eps, n_tokens, n_h, n_kv);
+    else
+        qk_norm_bwd_kernel<128><<<grid, 128, 0, st>>>((const bf16*)qkv_pre, (bf16*)dqkv, (const bf16*)q_norm_w, (const bf16*)k_norm_w,
+                                                      dqn_accum, dkn_accum, eps, n_tokens, n_h, n_kv);
+    return check_launch("tl_qk_norm_bwd");
 }
 
 int tl_ce_fwd_bwd(const void* logits, const int64_t* labels, float* loss_sum, int32_t* n_valid, void* dlogits,

@@ -14,7 +14,8 @@ its gradient are produced on the last stage by a fused lm_head + cross-entropy p
 [tokens, vocab] logits never exist in full.  The object returned as ``.loss`` is an autograd proxy on EVERY rank:
 ``loss.backward()`` runs that rank's part of the pipeline backward (SPMD equivalent of the autograd router).
 
-Not implemented (raises): Qwen3 q/k-norm backward (BASELINE config 4's model family) — planned next.
+Tied embeddings split over two ranks (Qwen2.5-0.5B at N > 1): the two copies' gradients are summed rank 0 <-> last
+rank before the optimizer step, so both copies take identical updates.
 """
 from __future__ import annotations
 
@@ -36,14 +37,16 @@ class StageTrainer:
     def __init__(self, stage):
         self.st = stage
         self.cfg = stage.cfg
-        if self.cfg.qk_norm:
-            raise NotImplementedError("training backward for Qwen3 q/k-norm is not implemented yet")
         self.p = stage.params
         self.layer_ids = stage.params.layer_ids
         dev = stage.device
         names = [f"l{li}.{n}" for li in self.layer_ids for n in ("ln1", "ln2")] + (["norm"] if stage.has_head else [])
         self.norm_acc: Dict[str, torch.Tensor] = {n: torch.zeros(self.cfg.hidden, dtype=torch.float32, device=dev)
                                                   for n in names}
+        if self.cfg.qk_norm:
+            for li in self.layer_ids:
+                for n in ("qn", "kn"):
+                    self.norm_acc[f"l{li}.{n}"] = torch.zeros(self.cfg.head_dim, dtype=torch.float32, device=dev)
         self.grp = stage.slots[0]                     # rope tables / scale come from the shard operator
         self.ctx: Dict[int, dict] = {}
         self.loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -68,8 +71,10 @@ class StageTrainer:
             s["q"] = torch.empty(N, cfg.q_dim, dtype=bf, device=dev)
             s["kc"] = torch.empty(b, cfg.n_kv_heads, S, cfg.head_dim, dtype=bf, device=dev)
             s["vc"] = torch.empty_like(s["kc"])
-            nat.rope_kv_fwd(qkv, s["q"], s["kc"], s["vc"], zero_pos, self.grp.cos, self.grp.sin, None, None, cfg.rms_eps,
-                            S, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim)
+            if cfg.qk_norm:
+                s["qkv"] = qkv                      # pre-norm q/k are needed by the q/k-norm backward
+            nat.rope_kv_fwd(qkv, s["q"], s["kc"], s["vc"], zero_pos, self.grp.cos, self.grp.sin, v.get(f"l{li}.qn"),
+                            v.get(f"l{li}.kn"), cfg.rms_eps, S, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim)
             s["attn"] = torch.empty(N, cfg.q_dim, dtype=bf, device=dev)
             s["lse"] = torch.empty(b, cfg.n_heads, S, dtype=torch.float32, device=dev)
             nat.attn_prefill_fwd(s["q"], s["kc"], s["vc"], s["attn"], s["lse"], b, S, 0, cfg.n_heads, cfg.n_kv_heads,
@@ -141,6 +146,9 @@ class StageTrainer:
                          cfg.n_kv_heads, cfg.head_dim, self.grp.scale)
             dqkv = torch.empty(N, cfg.qkv_dim, dtype=bf, device=dev)
             nat.rope_kv_bwd(dq, dk, dv, dqkv, self.grp.cos, self.grp.sin, S, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim)
+            if cfg.qk_norm:
+                nat.qk_norm_bwd(s["qkv"], dqkv, v[f"l{li}.qn"], v[f"l{li}.kn"], self.norm_acc[f"l{li}.qn"],
+                                self.norm_acc[f"l{li}.kn"], cfg.rms_eps, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim)
             dh1 = nat.gemm(dqkv, v[f"l{li}.wqkv"], flags=B_MN, N=H)
             nat.gemm(dqkv, s["h1"], out=g[f"l{li}.wqkv"], flags=A_MN | B_MN | ACC, M=cfg.qkv_dim, K=N, N=H)
             if cfg.qkv_bias:
@@ -255,6 +263,19 @@ def train_backward(dm, grad_scale: float = 1.0):
             tr.embed_backward(s["ids"][m * s["b"]:(m + 1) * s["b"]], dx)
     link.flush()
     tr.finish_backward()
+    if cfg.tied and dm.world > 1 and (link.first or link.last):
+        # module.py:1218-1265 ties lm_head to embed_tokens on the host; here the two copies live on different ranks
+        p = st.params
+        if link.last:
+            link.send_up(p.g["head"], 0)
+            link.flush()
+            link.recv_down(p.g["head"], 0)
+        else:
+            tmp = torch.empty_like(p.g["embed"])
+            link.recv_up(tmp, dm.world - 1)
+            nat.add_inplace(p.g["embed"].view(-1), tmp.view(-1))
+            link.send_down(p.g["embed"], dm.world - 1)
+            link.flush()
 
 
 class StageAdam:

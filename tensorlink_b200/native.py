@@ -55,6 +55,7 @@ _SIGS = {
                                c_void_p]),
     "tl_rope_kv_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                c_int, c_int, c_void_p]),
+    "tl_qk_norm_bwd": (c_int, [c_void_p] * 6 + [c_float, c_int, c_int, c_int, c_int, c_void_p]),
     "tl_attn_bwd_ws": (c_size_t, [c_int, c_int, c_int]),
     "tl_attn_bwd": (c_int, [c_void_p] * 10 + [c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "tl_ce_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p]),
@@ -393,3 +394,9 @@ def decode_step(jobs: DecodeJobList, M: int, sync_ws: torch.Tensor):
     require_device()
     _check(load().tl_decode_step(_p(jobs.dev), ctypes.cast(jobs.host, c_void_p), jobs.n, M, _p(sync_ws), _stream()),
            "tl_decode_step")
+
+
+def qk_norm_bwd(qkv_pre, dqkv, qn, kn, dqn_acc, dkn_acc, eps, n_h, n_kv, d):
+    require_device(); _bf16(qkv_pre, dqkv, qn, kn)
+    _check(load().tl_qk_norm_bwd(_p(qkv_pre), _p(dqkv), _p(qn), _p(kn), _p(dqn_acc), _p(dkn_acc), eps, dqkv.shape[0], n_h,
+                                 n_kv, d, _stream()), "tl_qk_norm_bwd")

@@ -51,6 +51,19 @@ def main(out_dir):
         ref = {k: v.cpu() for k, v in st.stage.params.hf_state_dict(grads=True).items()}
         res["loss_single"] = float(so.loss)
         torch.save(ref, os.path.join(out_dir, "ref_grads.pt"))
+    # tied embeddings split over the two ranks (Qwen2.5-0.5B layout): both copies must end up with the summed gradient
+    tc = C.TINY_QWEN2
+    tt = synthetic_tokens(tc, 2, 24).cuda()
+    dtie = DistributedModel(tc, training=True, n_pipelines=1, max_batch=2, max_seq=32, optimizer=torch.optim.Adam)
+    ot = dtie(tt if rank == 0 else None, labels=tt if rank == 0 else None)
+    ot.loss.backward()
+    key = "embed" if rank == 0 else "head"
+    torch.save(dtie.stage.params.g[key].cpu(), os.path.join(out_dir, f"tied{rank}.pt"))
+    if rank == 0:
+        s1 = DistributedModel(tc, training=True, n_pipelines=1, max_batch=2, max_seq=32, link=StageLink(0, 1),
+                              optimizer=torch.optim.Adam)
+        s1(tt, labels=tt).loss.backward()
+        torch.save(s1.stage.params.g["embed"].cpu(), os.path.join(out_dir, "tied_ref.pt"))
     torch.save(grads, os.path.join(out_dir, f"grads{rank}.pt"))
     torch.save(res, os.path.join(out_dir, f"rank{rank}.pt"))
     dist.barrier()

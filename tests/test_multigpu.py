@@ -35,3 +35,6 @@ def test_two_gpu_pipeline_equals_single_stage(tmp_path):
         assert len(g) > 10
         for k, v in g.items():
             assert torch.equal(v, ref[k]), f"rank {rank} grad {k} differs from the single-stage run"
+    t0, t1, tr = torch.load(tmp_path / "tied0.pt"), torch.load(tmp_path / "tied1.pt"), torch.load(tmp_path / "tied_ref.pt")
+    assert torch.equal(t0, t1)                                        # both copies of the tied weight see the same gradient
+    assert (t0.float() - tr.float()).norm() / tr.float().norm() < 5e-3   # = single-stage sum up to bf16 add order

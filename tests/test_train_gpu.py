@@ -167,7 +167,7 @@ def _oracle_grads(cfg, ids, dtype, attn="sdpa_math"):
     return float(loss), {k: v.grad for k, v in sd.items() if v.grad is not None}
 
 
-@pytest.mark.parametrize("cfg", [C.TINY_QWEN2, C.TINY_QWEN2_D128], ids=lambda c: c.name)
+@pytest.mark.parametrize("cfg", [C.TINY_QWEN2, C.TINY_QWEN2_D128, C.TINY_QWEN3], ids=lambda c: c.name)
 @pytest.mark.parametrize("n_mb", [1, 2])
 def test_training_step_vs_oracle_autograd(cfg, n_mb):
     from tensorlink_b200.ml import DistributedModel
@@ -185,11 +185,13 @@ def test_training_step_vs_oracle_autograd(cfg, n_mb):
     assert abs(float(out.loss) - loss32) <= max(2 * abs(loss16 - loss32), 2e-3)
     got = dm.stage.params.hf_state_dict(grads=True)
     worst = 0.0
-    for name in ("model.layers.0.self_attn.q_proj.weight", "model.layers.0.self_attn.k_proj.bias",
+    names = ["model.layers.0.self_attn.q_norm.weight", "model.layers.2.self_attn.k_norm.weight",
+             "model.layers.0.self_attn.k_proj.weight"] if cfg.qk_norm else ["model.layers.0.self_attn.k_proj.bias"]
+    for name in names + ["model.layers.0.self_attn.q_proj.weight",
                  "model.layers.1.self_attn.o_proj.weight", "model.layers.2.mlp.gate_proj.weight",
                  "model.layers.2.mlp.up_proj.weight", "model.layers.3.mlp.down_proj.weight",
                  "model.layers.0.input_layernorm.weight", "model.layers.3.post_attention_layernorm.weight",
-                 "model.norm.weight", "model.embed_tokens.weight"):
+                 "model.norm.weight", "model.embed_tokens.weight"]:
         e_ref = O.rel_l2(g16[name], g32[name])
         e_gpu = O.rel_l2(got[name].cpu(), g32[name])
         print(f"  {name}: gpu-vs-fp32 {e_gpu:.3e} oracle_bf16-vs-fp32 {e_ref:.3e}")
