@@ -159,14 +159,15 @@ int tl_swiglu_bwd(const void* gu, const void* dh, void* dgu, int M, int I, void*
 /* RMSNorm backward: dx = rstd*(dy*w - n*mean(dy*w*n)) (+ dx_add if non-NULL); dw_accum (fp32 [H]) += sum dy*n */
 int tl_rmsnorm_bwd(const void* x, const void* w, const void* dy, const float* rstd, const void* dx_add, void* dx,
                    float* dw_accum, int rows, int H, void* stream);
-/* RoPE backward + KV gather: dqkv[n, (n_h+2n_kv)*d] from dq[n, n_h*d] and dk/dv[B, n_kv, T_max, d] */
+/* RoPE backward + KV gather: dqkv[n, (n_h+2n_kv)*d] from dq[n, n_h*d] and dk/dv[B, n_h, T_max, d] (one partial per
+ * query head as written by tl_attn_bwd; the n_h/n_kv partials of a kv head are summed in fp32) */
 int tl_rope_kv_bwd(const void* dq, const void* dk, const void* dv, void* dqkv, const void* cos_tab,
                    const void* sin_tab, int n_tokens, int S, int n_h, int n_kv, int d, int T_max, void* stream);
 /* Qwen3 q/k-norm backward, in place on the q and k slices of dqkv[n, (n_h+2n_kv)*d] (gradient w.r.t. the
  * normalised vectors on entry, w.r.t. the pre-norm vectors on exit); gain gradients accumulate in fp32 [d] */
 int tl_qk_norm_bwd(const void* qkv_pre, void* dqkv, const void* q_norm_w, const void* k_norm_w, float* dqn_accum,
                    float* dkn_accum, float eps, int n_tokens, int n_h, int n_kv, int d, void* stream);
-/* attention backward (recompute P from lse): dq[B,S,n_h,d]; dk/dv[B,n_kv,T_max,d] rows < S */
+/* attention backward (recompute P from lse): dq[B,S,n_h,d]; dk/dv[B,n_h,T_max,d] rows < S, one partial per query head */
 size_t tl_attn_bwd_ws(int B, int S, int n_h);
 int tl_attn_bwd(const void* q, const void* k_cache, const void* v_cache, const void* out, const void* dout,
                 const float* lse, void* dq, void* dk, void* dv, void* workspace, size_t ws_bytes, int B, int S,
@@ -177,8 +178,8 @@ int tl_ce_fwd_bwd(const void* logits, const int64_t* labels, float* loss_sum, in
                   float grad_scale, int M, int V, void* stream);
 /* embedding backward: dtable[ids[n],:] += dout[n,:]  (bf16x2 atomics into the bf16 gradient) */
 int tl_embed_bwd(const int64_t* ids, const void* dout, void* dtable, int n_tokens, int H, int vocab, void* stream);
-/* bias gradient: db[N] (+)= sum_m dy[m,:N] (row pitch ld) */
-int tl_colsum(const void* dy, void* db, int M, int N, int ld, int accumulate, void* stream);
+/* bias gradient: db_accum[N] (fp32) += sum_m dy[m,:N] (row pitch ld) */
+int tl_colsum(const void* dy, float* db_accum, int M, int N, int ld, void* stream);
 /* dst[n] (+)= src[n]: fp32 accumulator into a bf16 gradient */
 int tl_f32_to_bf16_accum(const float* src, void* dst, size_t n, int accumulate, void* stream);
 /* a[n] += b[n] over bf16 (n %% 8 == 0) */

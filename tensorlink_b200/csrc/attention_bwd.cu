@@ -3,7 +3,8 @@
 //   pass 1  dQ tile    = sum_kv  dS · K          dS = P ∘ (dO·V^T − D) · scale      (parallel over query tiles)
 //   pass 2  dK,dV tile = sum_{q heads of the group, q tiles}  dS^T · Q ,  P^T · dO   (parallel over key tiles)
 // Warp-level mma.sync like the forward (attention is 3-6 % of the layer FLOPs at the BASELINE shapes).
-// q/o/do/dq: [B,S,n_h,d] token-major;  k/v/dk/dv: [B,n_kv,T_max,d];  lse/D: [B,n_h,S].
+// q/o/do/dq: [B,S,n_h,d] token-major;  k/v: [B,n_kv,T_max,d];  dk/dv: [B,n_h,T_max,d] (one partial per query head);
+// lse/D: [B,n_h,S].
 #include "common.cuh"
 
 namespace tl {
@@ -196,8 +197,10 @@ __global__ void __launch_bounds__(AB_THREADS) attn_bwd_dkv_kernel(const bf16* __
     float* sL = reinterpret_cast<float*>(sdO + 2 * AB_BQ * LDS);   // [2][64]  lse * log2e
     float* sD = sL + 2 * AB_BQ;                                    // [2][64]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
-    const int kt = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
-    const int n_rep = n_h / n_kv, kv0 = kt * AB_BKV;
+    // one CTA per (key tile, QUERY head): dK/dV come out as one partial per query head, summed over the GQA group by
+    // the RoPE backward kernel (7x more CTAs than looping the group inside one CTA, no atomics)
+    const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int n_rep = n_h / n_kv, kvh = h / n_rep, kv0 = kt * AB_BKV;
     const bf16* kg = k_cache + ((size_t)b * n_kv + kvh) * T_max * D;
     const bf16* vg = v_cache + ((size_t)b * n_kv + kvh) * T_max * D;
     for (int c = tid; c < AB_BKV * CPR; c += AB_THREADS) {
@@ -209,10 +212,10 @@ __global__ void __launch_bounds__(AB_THREADS) attn_bwd_dkv_kernel(const bf16* __
     }
     const int qt_first = kv0 / AB_BQ, n_qt = (S + AB_BQ - 1) / AB_BQ;
     const int per_head = n_qt - qt_first;
-    const int n_iter = per_head * n_rep;
+    const int n_iter = per_head;
     auto load_q = [&](int buf, int iter) {
-        const int r_ = iter / per_head, qt = qt_first + (iter - r_ * per_head);
-        const int h = kvh * n_rep + r_, q0 = qt * AB_BQ;
+        const int qt = qt_first + iter;
+        const int q0 = qt * AB_BQ;
         const bf16* qg = q + ((size_t)b * S) * n_h * D + (size_t)h * D;
         const bf16* dog = dout + ((size_t)b * S) * n_h * D + (size_t)h * D;
         for (int c = tid; c < AB_BQ * CPR; c += AB_THREADS) {
@@ -245,7 +248,7 @@ __global__ void __launch_bounds__(AB_THREADS) attn_bwd_dkv_kernel(const bf16* __
         cp_commit();
         cp_wait<1>();
         __syncthreads();
-        const int r_ = it / per_head, qt = qt_first + (it - r_ * per_head), q0 = qt * AB_BQ;
+        const int qt = qt_first + it, q0 = qt * AB_BQ;
         const bf16* sQb = sQ + buf * AB_BQ * LDS;
         const bf16* sdOb = sdO + buf * AB_BQ * LDS;
         const float* sLb = sL + buf * AB_BQ;
@@ -315,8 +318,8 @@ __global__ void __launch_bounds__(AB_THREADS) attn_bwd_dkv_kernel(const bf16* __
     for (int r = 0; r < 2; ++r) {
         const int key = key_row0 + r * 8;
         if (key >= S) continue;
-        bf16* dkd = dk + (((size_t)b * n_kv + kvh) * T_max + key) * D;
-        bf16* dvd = dv + (((size_t)b * n_kv + kvh) * T_max + key) * D;
+        bf16* dkd = dk + (((size_t)b * n_h + h) * T_max + key) * D;
+        bf16* dvd = dv + (((size_t)b * n_h + h) * T_max + key) * D;
 #pragma unroll
         for (int i = 0; i < D / 8; ++i) {
             *reinterpret_cast<uint32_t*>(dkd + i * 8 + 2 * t4) = pack_bf16(dka[i][2 * r], dka[i][2 * r + 1]);
@@ -344,7 +347,7 @@ int tl_attn_bwd(const void* q, const void* k_cache, const void* v_cache, const v
     float* Dv = (float*)workspace;
     const long long total = (long long)B * S * n_h;
     const int g0 = (int)((total * 32 + 255) / 256);
-    const dim3 g1((S + AB_BQ - 1) / AB_BQ, n_h, B), g2((S + AB_BKV - 1) / AB_BKV, n_kv, B);
+    const dim3 g1((S + AB_BQ - 1) / AB_BQ, n_h, B), g2((S + AB_BKV - 1) / AB_BKV, n_h, B);
     const size_t sm1 = (size_t)6 * 64 * (d + 8) * sizeof(bf16);
     const size_t sm2 = (size_t)6 * 64 * (d + 8) * sizeof(bf16) + 4 * 64 * sizeof(float);
     if (d == 64) {

@@ -43,7 +43,8 @@ __global__ void swiglu_bwd_kernel(const uint4* __restrict__ gu, const uint2* __r
 
 // ------------------------------------------------------------------------------------------------ RMSNorm backward
 // n = x*rstd, g = dy*w:  dx = rstd * (g - n * mean(g*n)) [+ dx_add];  dw[h] += sum_rows dy*n   (fp32 atomics)
-constexpr int NB_THREADS = 128, NB_MAXV = 8;
+constexpr int NB_THREADS = 128;
+template <int NB_MAXV>
 __global__ void __launch_bounds__(NB_THREADS) rmsnorm_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
                                                                    const bf16* __restrict__ dy, const float* __restrict__ rstd,
                                                                    const bf16* __restrict__ dx_add, bf16* __restrict__ dx,
@@ -57,6 +58,12 @@ __global__ void __launch_bounds__(NB_THREADS) rmsnorm_bwd_kernel(const bf16* __r
         for (int j = 0; j < 8; ++j) dwl[i][j] = 0.f;
     __shared__ float red[NB_THREADS / 32];
     const int r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    uint4 wreg[NB_MAXV];
+#pragma unroll
+    for (int i = 0; i < NB_MAXV; ++i) {
+        const int idx = threadIdx.x + i * NB_THREADS;
+        wreg[i] = idx < nvec ? reinterpret_cast<const uint4*>(w)[idx] : make_uint4(0, 0, 0, 0);
+    }
     for (int row = r0; row < r1; ++row) {
         const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * H);
         const uint4* dr = reinterpret_cast<const uint4*>(dy + (size_t)row * H);
@@ -67,7 +74,7 @@ __global__ void __launch_bounds__(NB_THREADS) rmsnorm_bwd_kernel(const bf16* __r
         for (int i = 0; i < NB_MAXV; ++i) {
             const int idx = threadIdx.x + i * NB_THREADS;
             if (idx < nvec) {
-                const uint4 xv = xr[idx], dv = dr[idx], wv = reinterpret_cast<const uint4*>(w)[idx];
+                const uint4 xv = xr[idx], dv = dr[idx], wv = wreg[i];
                 const uint32_t* x32 = reinterpret_cast<const uint32_t*>(&xv);
                 const uint32_t* d32 = reinterpret_cast<const uint32_t*>(&dv);
                 const uint32_t* w32 = reinterpret_cast<const uint32_t*>(&wv);
@@ -135,13 +142,21 @@ __global__ void __launch_bounds__(128) rope_kv_bwd_kernel(const bf16* __restrict
     const int b = n / S, pos = n - b * S;
     bf16* dst = dqkv + (size_t)n * heads * D + (size_t)h * D;
     const bool is_q = h < n_h, is_k = !is_q && h < n_h + n_kv;
+    // dk / dv arrive as one partial per QUERY head ([B, n_h, T_max, d]); the n_rep partials of a kv head are summed here
+    const int n_rep = n_h / n_kv;
+    const int kvh = is_q ? 0 : (is_k ? h - n_h : h - n_h - n_kv);
     const bf16* src = is_q ? dq + (size_t)n * n_h * D + (size_t)h * D
-                           : (is_k ? dk + (((size_t)b * n_kv + (h - n_h)) * T_max + pos) * D
-                                   : dv + (((size_t)b * n_kv + (h - n_h - n_kv)) * T_max + pos) * D);
+                           : (is_k ? dk : dv) + (((size_t)b * n_h + (size_t)kvh * n_rep) * T_max + pos) * D;
 #pragma unroll
     for (int p = 0; p < PAIRS; ++p) {
         const int i = lane + 32 * p;
-        const float d1 = bf2f(src[i]), d2 = bf2f(src[i + HALF]);
+        float d1 = bf2f(src[i]), d2 = bf2f(src[i + HALF]);
+        if (!is_q) {
+            for (int r = 1; r < n_rep; ++r) {
+                d1 += bf2f(src[(size_t)r * T_max * D + i]);
+                d2 += bf2f(src[(size_t)r * T_max * D + i + HALF]);
+            }
+        }
         if (!is_q && !is_k) {
             dst[i] = f2bf(d1);
             dst[i + HALF] = f2bf(d2);
@@ -281,12 +296,13 @@ __global__ void embed_bwd_kernel(const int64_t* __restrict__ ids, const bf16* __
 }
 
 // ------------------------------------------------------------------------------------------------ column sum (bias grad)
-// db[c] (+)= sum_m dy[m, c];  block = 32x8 threads handles 64 columns (bf16x2 per thread.x), rows strided over y
-__global__ void colsum_kernel(const bf16* __restrict__ dy, bf16* __restrict__ db, int M, int N, int ld, int accumulate) {
+// db_accum[c] += sum_m dy[m, c]   (fp32 atomics).  block = 32x8 threads: 64 columns x a 256-row slab
+__global__ void colsum_kernel(const bf16* __restrict__ dy, float* __restrict__ db, int M, int N, int ld) {
     const int c2 = blockIdx.x * 32 + threadIdx.x;      // bf16x2 column index
     float a0 = 0.f, a1 = 0.f;
+    const int m0 = blockIdx.y * 256, m1 = min(M, m0 + 256);
     if (2 * c2 < N) {
-        for (int m = blockIdx.y * blockDim.y + threadIdx.y; m < M; m += gridDim.y * blockDim.y) {
+        for (int m = m0 + threadIdx.y; m < m1; m += 8) {
             const uint32_t u = *reinterpret_cast<const uint32_t*>(dy + (size_t)m * ld + 2 * c2);
             a0 += bf16_lo(u);
             a1 += bf16_hi(u);
@@ -299,12 +315,8 @@ __global__ void colsum_kernel(const bf16* __restrict__ dy, bf16* __restrict__ db
     if (threadIdx.y == 0 && 2 * c2 < N) {
 #pragma unroll
         for (int j = 1; j < 8; ++j) { a0 += s0[j][threadIdx.x]; a1 += s1[j][threadIdx.x]; }
-        // gridDim.y partial sums are combined with fp32 atomics on a scratch-free path: gridDim.y == 1 by launch
-        if (accumulate) {
-            a0 += bf2f(db[2 * c2]);
-            a1 += bf2f(db[2 * c2 + 1]);
-        }
-        *reinterpret_cast<uint32_t*>(db + 2 * c2) = pack_bf16(a0, a1);
+        atomicAdd(&db[2 * c2], a0);
+        atomicAdd(&db[2 * c2 + 1], a1);
     }
 }
 
@@ -377,13 +389,21 @@ int tl_swiglu_bwd(const void* gu, const void* dh, void* dgu, int M, int I, void*
 int tl_rmsnorm_bwd(const void* x, const void* w, const void* dy, const float* rstd, const void* dx_add, void* dx,
                    float* dw_accum, int rows, int H, void* stream) {
     using namespace tl;
-    TL_REQUIRE(H % 8 == 0 && H <= NB_THREADS * NB_MAXV * 8, TL_ERR_INVALID, "tl_rmsnorm_bwd: unsupported H=%d", H);
+    TL_REQUIRE(H % 8 == 0 && H <= NB_THREADS * 8 * 8, TL_ERR_INVALID, "tl_rmsnorm_bwd: unsupported H=%d", H);
     if (rows == 0) return TL_OK;
-    int rpb = (rows + sm_count() * 4 - 1) / (sm_count() * 4);
+    int rpb = (rows + sm_count() * 2 - 1) / (sm_count() * 2);
     if (rpb < 1) rpb = 1;
     const int grid = (rows + rpb - 1) / rpb;
-    rmsnorm_bwd_kernel<<<grid, NB_THREADS, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)w, (const bf16*)dy, rstd,
-                                                                      (const bf16*)dx_add, (bf16*)dx, dw_accum, rows, H, rpb);
+    const int nv = ((H >> 3) + NB_THREADS - 1) / NB_THREADS;
+    cudaStream_t st = (cudaStream_t)stream;
+#define TL_NB(MV)                                                                                                       \
+    rmsnorm_bwd_kernel<MV><<<grid, NB_THREADS, 0, st>>>((const bf16*)x, (const bf16*)w, (const bf16*)dy, rstd,          \
+                                                       (const bf16*)dx_add, (bf16*)dx, dw_accum, rows, H, rpb)
+    if (nv <= 1) TL_NB(1);
+    else if (nv <= 2) TL_NB(2);
+    else if (nv <= 4) TL_NB(4);
+    else TL_NB(8);
+#undef TL_NB
     return check_launch("tl_rmsnorm_bwd");
 }
 
@@ -439,11 +459,12 @@ int tl_embed_bwd(const int64_t* ids, const void* dout, void* dtable, int n_token
     return check_launch("tl_embed_bwd");
 }
 
-int tl_colsum(const void* dy, void* db, int M, int N, int ld, int accumulate, void* stream) {
+int tl_colsum(const void* dy, float* db_accum, int M, int N, int ld, void* stream) {
     using namespace tl;
     TL_REQUIRE(N % 2 == 0 && ld % 2 == 0, TL_ERR_INVALID, "tl_colsum: N/ld must be even");
-    const dim3 grid((N / 2 + 31) / 32, 1), block(32, 8);
-    colsum_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const bf16*)dy, (bf16*)db, M, N, ld, accumulate);
+    if (M == 0) return TL_OK;
+    const dim3 grid((N / 2 + 31) / 32, (M + 255) / 256), block(32, 8);
+    colsum_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const bf16*)dy, db_accum, M, N, ld);
     return check_launch("tl_colsum");
 }
 

@@ -43,6 +43,9 @@ class StageTrainer:
         names = [f"l{li}.{n}" for li in self.layer_ids for n in ("ln1", "ln2")] + (["norm"] if stage.has_head else [])
         self.norm_acc: Dict[str, torch.Tensor] = {n: torch.zeros(self.cfg.hidden, dtype=torch.float32, device=dev)
                                                   for n in names}
+        if self.cfg.qkv_bias:
+            for li in self.layer_ids:
+                self.norm_acc[f"l{li}.bqkv"] = torch.zeros(self.cfg.qkv_dim, dtype=torch.float32, device=dev)
         if self.cfg.qk_norm:
             for li in self.layer_ids:
                 for n in ("qn", "kn"):
@@ -140,8 +143,8 @@ class StageTrainer:
             d_attn = nat.gemm(d_xmid, v[f"l{li}.wo"], flags=B_MN, N=cfg.q_dim)
             nat.gemm(d_xmid, s["attn"], out=g[f"l{li}.wo"], flags=A_MN | B_MN | ACC, M=H, K=N, N=cfg.q_dim)
             dq = torch.empty(N, cfg.q_dim, dtype=bf, device=dev)
-            dk = torch.empty_like(s["kc"])
-            dv = torch.empty_like(s["vc"])
+            dk = torch.empty(b, cfg.n_heads, S, cfg.head_dim, dtype=bf, device=dev)     # one partial per query head
+            dv = torch.empty_like(dk)
             nat.attn_bwd(s["q"], s["kc"], s["vc"], s["attn"], d_attn, s["lse"], dq, dk, dv, ws, b, S, cfg.n_heads,
                          cfg.n_kv_heads, cfg.head_dim, self.grp.scale)
             dqkv = torch.empty(N, cfg.qkv_dim, dtype=bf, device=dev)
@@ -152,7 +155,7 @@ class StageTrainer:
             dh1 = nat.gemm(dqkv, v[f"l{li}.wqkv"], flags=B_MN, N=H)
             nat.gemm(dqkv, s["h1"], out=g[f"l{li}.wqkv"], flags=A_MN | B_MN | ACC, M=cfg.qkv_dim, K=N, N=H)
             if cfg.qkv_bias:
-                nat.colsum(dqkv, g[f"l{li}.bqkv"], accumulate=True)
+                nat.colsum(dqkv, self.norm_acc[f"l{li}.bqkv"])
             dx = torch.empty(N, H, dtype=bf, device=dev)
             nat.rmsnorm_bwd(s["x_in"], v[f"l{li}.ln1"], dh1, s["rstd1"], dx, self.norm_acc[f"l{li}.ln1"], dx_add=d_xmid)
             dy = dx

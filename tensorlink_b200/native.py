@@ -60,7 +60,7 @@ _SIGS = {
     "tl_attn_bwd": (c_int, [c_void_p] * 10 + [c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "tl_ce_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p]),
     "tl_embed_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
-    "tl_colsum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "tl_colsum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "tl_f32_to_bf16_accum": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "tl_add_inplace": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "tl_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float, c_float, c_float,
@@ -337,10 +337,11 @@ def embed_bwd(ids, dout, dtable):
     _check(load().tl_embed_bwd(_p(ids), _p(dout), _p(dtable), ids.numel(), H, V, _stream()), "tl_embed_bwd")
 
 
-def colsum(dy, db, accumulate: bool):
-    require_device(); _bf16(db)
+def colsum(dy, db_accum):
+    require_device()
+    assert db_accum.dtype == torch.float32
     M, N = dy.shape
-    _check(load().tl_colsum(_p(dy), _p(db), M, N, dy.stride(0), int(accumulate), _stream()), "tl_colsum")
+    _check(load().tl_colsum(_p(dy), _p(db_accum), M, N, dy.stride(0), _stream()), "tl_colsum")
 
 
 def f32_to_bf16_accum(src, dst, accumulate: bool):

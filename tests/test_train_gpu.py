@@ -64,18 +64,22 @@ def test_rope_kv_bwd(nat, cfg):
     B, S, d, n_h, n_kv = 2, 19, cfg.head_dim, cfg.n_heads, cfg.n_kv_heads
     q = rnd(B, n_h, S, d, seed=7).float().requires_grad_()
     k = rnd(B, n_kv, S, d, seed=8).float().requires_grad_()
-    dq, dk, dv = rnd(B, S, n_h, d, seed=9), rnd(B, n_kv, S, d, seed=10), rnd(B, n_kv, S, d, seed=11)
+    n_rep = n_h // n_kv
+    dq = rnd(B, S, n_h, d, seed=9)
+    dk_p, dv_p = rnd(B, n_h, S, d, seed=10), rnd(B, n_h, S, d, seed=11)          # one partial per query head
+    dk = dk_p.float().view(B, n_kv, n_rep, S, d).sum(2)
+    dv = dv_p.float().view(B, n_kv, n_rep, S, d).sum(2)
     cos, sin = O.rope_tables(cfg, torch.arange(S)[None].expand(B, -1), torch.bfloat16)
     qr, kr = O.apply_rope(q, k, cos.float(), sin.float())
     (qr * dq.transpose(1, 2).float()).sum().backward(retain_graph=True)
     (kr * dk.float()).sum().backward()
     ct, st = nat.rope_table(O.rope_inv_freq(cfg).cuda(), 64)
     dqkv = torch.empty(B * S, cfg.qkv_dim, dtype=torch.bfloat16, device="cuda")
-    nat.rope_kv_bwd(dq.cuda().reshape(B * S, -1), dk.cuda(), dv.cuda(), dqkv, ct, st, S, n_h, n_kv, d)
+    nat.rope_kv_bwd(dq.cuda().reshape(B * S, -1), dk_p.cuda(), dv_p.cuda(), dqkv, ct, st, S, n_h, n_kv, d)
     got = dqkv.cpu().view(B, S, n_h + 2 * n_kv, d)
     assert O.rel_l2(got[:, :, :n_h].transpose(1, 2), q.grad) <= TOL
     assert O.rel_l2(got[:, :, n_h:n_h + n_kv].transpose(1, 2), k.grad) <= TOL
-    assert torch.equal(got[:, :, n_h + n_kv:].transpose(1, 2), dv)
+    assert O.rel_l2(got[:, :, n_h + n_kv:].transpose(1, 2), dv) <= TOL
 
 
 @pytest.mark.parametrize("B,S,n_h,n_kv,d", [(2, 64, 4, 2, 64), (1, 100, 14, 2, 64), (2, 130, 4, 2, 128), (1, 257, 8, 8, 128)])
@@ -96,13 +100,15 @@ def test_attn_bwd(nat, B, S, n_h, n_kv, d):
     lse = torch.empty(B, n_h, S, dtype=torch.float32, device="cuda")
     nat.attn_prefill_fwd(q.cuda(), kc, vc, out, lse, B, S, 0, n_h, n_kv, d, d ** -0.5)
     dq = torch.empty(B, S, n_h, d, dtype=torch.bfloat16, device="cuda")
-    dk = torch.zeros_like(kc)
-    dv = torch.zeros_like(vc)
+    dk = torch.zeros(B, n_h, T_max, d, dtype=torch.bfloat16, device="cuda")          # one partial per query head
+    dv = torch.zeros_like(dk)
     ws = torch.empty(nat.attn_bwd_ws(B, S, n_h), dtype=torch.uint8, device="cuda")
     nat.attn_bwd(q.cuda(), kc, vc, out, do.cuda(), lse, dq, dk, dv, ws, B, S, n_h, n_kv, d, d ** -0.5)
     assert O.rel_l2(dq.cpu(), qf.grad) <= TOL
-    assert O.rel_l2(dk.cpu()[:, :, :S], kf.grad) <= TOL
-    assert O.rel_l2(dv.cpu()[:, :, :S], vf.grad) <= TOL
+    dks = dk.cpu().float().view(B, n_kv, n_rep, T_max, d).sum(2)
+    dvs = dv.cpu().float().view(B, n_kv, n_rep, T_max, d).sum(2)
+    assert O.rel_l2(dks[:, :, :S], kf.grad) <= TOL
+    assert O.rel_l2(dvs[:, :, :S], vf.grad) <= TOL
     assert dk.cpu()[:, :, S:].abs().sum() == 0
 
 
@@ -133,9 +139,9 @@ def test_embed_bwd_colsum_add(nat):
     ref = torch.zeros(16, 64).index_add_(0, ids.view(-1), dout.float())
     assert O.rel_l2(dt.cpu(), ref) <= TOL
     dy = rnd(300, 1152, seed=18)
-    db = torch.ones(1152, dtype=torch.bfloat16, device="cuda")
-    nat.colsum(dy.cuda(), db, accumulate=True)
-    assert O.rel_l2(db.cpu(), 1 + dy.float().sum(0)) <= TOL
+    db = torch.ones(1152, dtype=torch.float32, device="cuda")
+    nat.colsum(dy.cuda(), db)
+    assert O.rel_l2(db.cpu(), 1 + dy.float().sum(0)) <= 1e-5
     a, b = rnd(4096, seed=19), rnd(4096, seed=20)
     ad = a.cuda()
     nat.add_inplace(ad, b.cuda())
