@@ -127,6 +127,84 @@ __global__ void __launch_bounds__(NB_THREADS) rmsnorm_bwd_kernel(const bf16* __r
     }
 }
 
+
+// narrow rows (H <= 1024): one WARP per row, 4 rows in flight per CTA, no block barriers in the row loop
+constexpr int NBW_MAXV = 4;
+__global__ void __launch_bounds__(NB_THREADS) rmsnorm_bwd_warp_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                                                        const bf16* __restrict__ dy, const float* __restrict__ rstd,
+                                                                        const bf16* __restrict__ dx_add, bf16* __restrict__ dx,
+                                                                        float* __restrict__ dw_accum, int rows, int H) {
+    const int nvec = H >> 3, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gw = blockIdx.x * (NB_THREADS / 32) + warp, nw = gridDim.x * (NB_THREADS / 32);
+    float dwl[NBW_MAXV][8];
+    uint4 wreg[NBW_MAXV];
+#pragma unroll
+    for (int i = 0; i < NBW_MAXV; ++i) {
+        const int idx = lane + 32 * i;
+        wreg[i] = idx < nvec ? reinterpret_cast<const uint4*>(w)[idx] : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dwl[i][j] = 0.f;
+    }
+    for (int row = gw; row < rows; row += nw) {
+        const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * H);
+        const uint4* dr = reinterpret_cast<const uint4*>(dy + (size_t)row * H);
+        const float rs = rstd[row];
+        float nv[NBW_MAXV][8], gv[NBW_MAXV][8];
+        float dot = 0.f;
+#pragma unroll
+        for (int i = 0; i < NBW_MAXV; ++i) {
+            const int idx = lane + 32 * i;
+            if (idx < nvec) {
+                const uint4 xv = xr[idx], dv = dr[idx];
+                const uint32_t* x32 = reinterpret_cast<const uint32_t*>(&xv);
+                const uint32_t* d32 = reinterpret_cast<const uint32_t*>(&dv);
+                const uint32_t* w32 = reinterpret_cast<const uint32_t*>(&wreg[i]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float n0 = bf16_lo(x32[j]) * rs, n1 = bf16_hi(x32[j]) * rs;
+                    const float d0 = bf16_lo(d32[j]), d1 = bf16_hi(d32[j]);
+                    nv[i][2 * j] = n0; nv[i][2 * j + 1] = n1;
+                    gv[i][2 * j] = d0 * bf16_lo(w32[j]); gv[i][2 * j + 1] = d1 * bf16_hi(w32[j]);
+                    dot += gv[i][2 * j] * n0 + gv[i][2 * j + 1] * n1;
+                    dwl[i][2 * j] += d0 * rbf(n0); dwl[i][2 * j + 1] += d1 * rbf(n1);
+                }
+            }
+        }
+        const float mean = warp_sum(dot) / (float)H;
+        uint4* outr = reinterpret_cast<uint4*>(dx + (size_t)row * H);
+#pragma unroll
+        for (int i = 0; i < NBW_MAXV; ++i) {
+            const int idx = lane + 32 * i;
+            if (idx < nvec) {
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = rbf(rs * (gv[i][j] - nv[i][j] * mean));
+                if (dx_add) {
+                    const uint4 av = reinterpret_cast<const uint4*>(dx_add + (size_t)row * H)[idx];
+                    const uint32_t* a32 = reinterpret_cast<const uint32_t*>(&av);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { o[2 * j] += bf16_lo(a32[j]); o[2 * j + 1] += bf16_hi(a32[j]); }
+                }
+                outr[idx] = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+            }
+        }
+    }
+    if (dw_accum) {
+        __shared__ float sdw[NB_THREADS / 32][NBW_MAXV * 32 * 8 + 1];
+#pragma unroll
+        for (int i = 0; i < NBW_MAXV; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sdw[warp][(lane + 32 * i) * 8 + j] = dwl[i][j];
+        __syncthreads();
+        for (int c = threadIdx.x; c < H; c += NB_THREADS) {
+            float t = 0.f;
+#pragma unroll
+            for (int wv = 0; wv < NB_THREADS / 32; ++wv) t += sdw[wv][c];
+            atomicAdd(&dw_accum[c], t);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ RoPE backward
 // one warp per (token, head): inverse rotation of dq / dk, plain gather of dv -> dqkv[n, (n_h+2n_kv)*d]
 template <int D>
@@ -396,6 +474,14 @@ int tl_rmsnorm_bwd(const void* x, const void* w, const void* dy, const float* rs
     const int grid = (rows + rpb - 1) / rpb;
     const int nv = ((H >> 3) + NB_THREADS - 1) / NB_THREADS;
     cudaStream_t st = (cudaStream_t)stream;
+    if ((H >> 3) <= 32 * NBW_MAXV) {
+        int g = (rows + 3) / 4;
+        const int cap = sm_count() * 4;
+        if (g > cap) g = cap;
+        rmsnorm_bwd_warp_kernel<<<g, NB_THREADS, 0, st>>>((const bf16*)x, (const bf16*)w, (const bf16*)dy, rstd,
+                                                          (const bf16*)dx_add, (bf16*)dx, dw_accum, rows, H);
+        return check_launch("tl_rmsnorm_bwd");
+    }
 #define TL_NB(MV)                                                                                                       \
     rmsnorm_bwd_kernel<MV><<<grid, NB_THREADS, 0, st>>>((const bf16*)x, (const bf16*)w, (const bf16*)dy, rstd,          \
                                                        (const bf16*)dx_add, (bf16*)dx, dw_accum, rows, H, rpb)
