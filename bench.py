@@ -193,7 +193,7 @@ def measure_training(args, N, rank, world, tf_peak, peak_kind):
     cfg = get_config(args.train_model)
     B, S = args.train_batch * N, args.train_seq
     dm = DistributedModel(args.train_model, training=True, n_pipelines=N, max_batch=B, max_seq=S, init="device",
-                          optimizer=torch.optim.Adam, max_tokens=8)
+                          optimizer=torch.optim.Adam, max_tokens=8, balanced_plan=N > 1)
     opt = dm.create_optimizer(lr=1e-4)
     ids_host = synthetic_tokens(cfg, B, S).pin_memory()
 
@@ -270,6 +270,13 @@ def main():
     ap.add_argument("--train-seq", type=int, default=512)
     args = ap.parse_args()
     name, prompt, new = WORKLOADS[args.workload]
+    # exactly ONE line goes to stdout: NCCL / torch banners printed during start-up are diverted to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     N = max(args.gpus, 1)
@@ -281,7 +288,8 @@ def main():
     base = {"metric": "generate tokens/sec", "unit": "tokens/s", "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_desc, "model": name, "global_batch": rows, "prompt_len": prompt,
-                       "new_tokens": new, "parallelism": f"pp{N}", "weights": "random-init (seeded, on device)",
+                       "new_tokens": new, "parallelism": f"pp{N}" + (" (byte-balanced layer split: lm_head counted on the last stage)" if N > 1 else ""),
+                       "weights": "random-init (seeded, on device)",
                        "l2": "inputs larger than L2: every decode step streams the stage's weights "
                              f"({2 * cfg.total_params() / 1e9:.1f} GB total) from HBM"}}
 
@@ -300,7 +308,7 @@ def main():
                     cpu_baseline={"value": val, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
                     e2e={"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                     gpu_launches=0)
-        print(json.dumps(line), flush=True)
+        emit(line)
         return 0
 
     import torch
@@ -313,7 +321,7 @@ def main():
     else:
         torch.cuda.set_device(0)
     dm = DistributedModel(name, training=False, n_pipelines=N, max_batch=rows, max_seq=prompt + new + 8,
-                          init="device", max_tokens=args.rows_per_gpu * prompt)
+                          init="device", max_tokens=args.rows_per_gpu * prompt, balanced_plan=N > 1)
     ids_host = synthetic_tokens(cfg, rows, prompt).pin_memory()
     ids_dev = ids_host.to(dm.device)
 
@@ -395,7 +403,7 @@ def main():
             ref.run(new, 1)
             v, sample = ref.run(new, 4)
             line["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": ref.threads, "kind": "port", "sample": sample}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -8,17 +8,15 @@
 // the MMAs of tile i+1.  Operands may be K-major (row-major [rows, K]) or MN-major (row-major [K, rows]) so the
 // same kernel serves forward (x·W^T), dgrad (dy·W) and wgrad (dy^T·x) without transposes.
 // Tensor-core roofline: 2*M*N*K flops per launch.
-#include <cuda.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <unordered_map>
 
-#include "common.cuh"
+#include "gemm_common.cuh"
 
 namespace tl {
 
-constexpr int BM = 128;
-constexpr int BK = 64;
 constexpr int GEMM_THREADS = 192;
 
 // ---------------------------------------------------------------------------------------- tensor maps (host)
@@ -62,8 +60,8 @@ struct MapKeyHash {
 };
 
 // 2-D bf16 row-major tensor [outer, inner] with leading dimension ld (elements); 128B-swizzled boxes
-static int make_tensor_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
-                           uint32_t box_inner, uint32_t box_outer) {
+int make_tensor_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                    uint32_t box_outer) {
     static std::mutex mu;
     static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
     MapKey key{ptr, inner, outer, ld, box_inner, box_outer};
@@ -214,8 +212,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int quarter = warp & 3;                  // TMEM lanes [32*quarter, 32*quarter+32)
         int acc = 0;
         uint32_t acc_phase = 0;
-        const bool swiglu = flags & TL_EPI_SWIGLU;
-        const bool out_f32 = flags & TL_EPI_OUT_F32;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
             mbar_wait(&tmem_full[acc], acc_phase);
@@ -228,95 +224,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tmem_ld32(taddr + (uint32_t)(c * 32), r);
                 tmem_ld_wait();
                 const int col0 = n0 + c * 32;
-                if (row < M && col0 < N) {
-                    float v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    const int ncols = min(32, N - col0);
-                    if (flags & TL_EPI_BIAS) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < ncols) v[j] += bf2f(bias[col0 + j]);
-                    }
-                    if (swiglu) {
-                        // interleaved (gate, up) column pairs -> 16 outputs
-                        bf16* dst = reinterpret_cast<bf16*>(Cv) + (size_t)row * ldc + (col0 >> 1);
-                        uint32_t o[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float g0 = rbf(v[4 * j]), u0 = rbf(v[4 * j + 1]);
-                            const float g1 = rbf(v[4 * j + 2]), u1 = rbf(v[4 * j + 3]);
-                            o[j] = pack_bf16(rbf(silu_f(g0)) * u0, rbf(silu_f(g1)) * u1);
-                        }
-                        if (ncols == 32) {
-                            reinterpret_cast<uint4*>(dst)[0] = make_uint4(o[0], o[1], o[2], o[3]);
-                            reinterpret_cast<uint4*>(dst)[1] = make_uint4(o[4], o[5], o[6], o[7]);
-                        } else {
-                            for (int j = 0; j < ncols / 2; ++j)
-                                dst[j] = reinterpret_cast<bf16*>(o)[j];
-                        }
-                    } else if (out_f32) {
-                        float* dst = reinterpret_cast<float*>(Cv) + (size_t)row * ldc + col0;
-                        if (flags & TL_EPI_ACCUM) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (j < ncols) v[j] += dst[j];
-                        }
-                        if (ncols == 32) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                        } else {
-                            for (int j = 0; j < ncols; ++j) dst[j] = v[j];
-                        }
-                    } else {
-                        bf16* dst = reinterpret_cast<bf16*>(Cv) + (size_t)row * ldc + col0;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = rbf(v[j]);     // the Linear's own bf16 output
-                        if (flags & TL_EPI_RESIDUAL) {
-                            const bf16* rs = residual + (size_t)row * ldr + col0;
-                            if (ncols == 32) {
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    const uint4 u = reinterpret_cast<const uint4*>(rs)[q];
-                                    const uint32_t* u32 = reinterpret_cast<const uint32_t*>(&u);
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j) {
-                                        v[8 * q + 2 * j] += bf16_lo(u32[j]);
-                                        v[8 * q + 2 * j + 1] += bf16_hi(u32[j]);
-                                    }
-                                }
-                            } else {
-                                for (int j = 0; j < ncols; ++j) v[j] += bf2f(rs[j]);
-                            }
-                        }
-                        if (flags & TL_EPI_ACCUM) {
-                            if (ncols == 32) {
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    const uint4 u = reinterpret_cast<const uint4*>(dst)[q];
-                                    const uint32_t* u32 = reinterpret_cast<const uint32_t*>(&u);
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j) {
-                                        v[8 * q + 2 * j] += bf16_lo(u32[j]);
-                                        v[8 * q + 2 * j + 1] += bf16_hi(u32[j]);
-                                    }
-                                }
-                            } else {
-                                for (int j = 0; j < ncols; ++j) v[j] += bf2f(dst[j]);
-                            }
-                        }
-                        if (ncols == 32) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                reinterpret_cast<uint4*>(dst)[q] =
-                                    make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
-                                               pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
-                        } else {
-                            for (int j = 0; j < ncols; ++j) dst[j] = f2bf(v[j]);
-                        }
-                    }
-                }
+                gemm_epilogue_chunk(r, Cv, row, col0, M, N, ldc, bias, residual, ldr, flags);
             }
             tcgen05_fence_before();
             __syncwarp();
@@ -370,6 +278,18 @@ static int dispatch_major(bool a_mn, bool b_mn, const void* A, const void* B, vo
     return launch_gemm<BN, true, true>(A, B, C, M, N, K, lda, ldb, ldc, bias, residual, flags, st);
 }
 
+int gemm2_dispatch(bool a_mn, bool b_mn, const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
+                   const void* bias, const void* residual, int flags, cudaStream_t st);
+
+static bool use_2cta() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("TL_GEMM_IMPL");
+        v = (e && e[0] == '1') ? 0 : 1;      // TL_GEMM_IMPL=1cta forces the single-CTA kernel (A/B tests)
+    }
+    return v == 1;
+}
+
 }  // namespace tl
 
 extern "C" int tl_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
@@ -391,6 +311,10 @@ extern "C" int tl_gemm_bf16(const void* A, const void* B, void* C, int M, int N,
     TL_REQUIRE(lda >= (a_mn ? M : K) && ldb >= (b_mn ? N : K), TL_ERR_INVALID, "tl_gemm_bf16: lda/ldb too small");
     TL_REQUIRE((!a_mn || M % 8 == 0), TL_ERR_INVALID, "tl_gemm_bf16: MN-major A needs M %% 8 == 0");
     cudaStream_t st = (cudaStream_t)stream;
+    // 256x256 tiles on CTA pairs (cta_group::2) when there are enough of them to fill the 74 pairs
+    const long long tiles2 = (long long)((M + 255) / 256) * ((N + 255) / 256);
+    if (use_2cta() && M > 128 && N >= 256 && tiles2 >= (long long)(sm_count() / 2))
+        return gemm2_dispatch(a_mn, b_mn, A, B, C, M, N, K, lda, ldb, ldc, bias, residual, flags, st);
     // 128x256 tiles when they still fill the machine, else 128x128
     const long long tiles256 = (long long)((M + BM - 1) / BM) * ((N + 255) / 256);
     const bool use256 = (N >= 256) && tiles256 >= (long long)sm_count();

@@ -124,6 +124,31 @@ def test_gemm_mn_major_operands(nat, M, N, K):
         assert O.rel_l2(got, ref) <= 1e-5, "A and B MN-major"
 
 
+@pytest.mark.parametrize("M,N,K", [(2048, 2560, 320), (2050, 2568, 200), (4096, 4864, 896), (2304, 2304, 64)])
+def test_gemm_2cta_tiles(nat, M, N, K):
+    """Shapes with >= 74 tiles of 256x256: served by the cta_group::2 kernel (gemm2.cu); all epilogues and majors."""
+    a, w = rnd(M, K, seed=31), rnd(N, K, seed=32, std=0.05)
+    b, r = rnd(N, seed=33, std=0.5), rnd(M, N, seed=34)
+    ref = a.double() @ w.double().t()
+    got = nat.gemm(dev(a), dev(w), flags=nat.EPI_OUT_F32).cpu()
+    assert O.rel_l2(got, ref) <= 1e-5
+    assert O.rel_l2(nat.gemm(dev(a), dev(w), bias=dev(b), residual=dev(r)).cpu(), r + F.linear(a, w, b)) <= TOL
+    got = nat.gemm(dev(a), dev(w.t().contiguous()), flags=nat.B_MN_MAJOR | nat.EPI_OUT_F32, N=N).cpu()
+    assert O.rel_l2(got, ref) <= 1e-5, "B MN-major"
+    if M % 8 == 0:
+        got = nat.gemm(dev(a.t().contiguous()), dev(w.t().contiguous()),
+                       flags=nat.A_MN_MAJOR | nat.B_MN_MAJOR | nat.EPI_OUT_F32, M=M, K=K, N=N).cpu()
+        assert O.rel_l2(got, ref) <= 1e-5, "A and B MN-major"
+        c0 = rnd(M, N, seed=35)
+        c = dev(c0.clone())
+        nat.gemm(dev(a.t().contiguous()), dev(w), out=c, flags=nat.A_MN_MAJOR | nat.EPI_ACCUM, M=M, K=K)
+        assert O.rel_l2(c.cpu(), c0 + F.linear(a, w)) <= TOL
+    if N % 16 == 0:
+        got = nat.gemm(dev(a), dev(w), flags=nat.EPI_SWIGLU).cpu()
+        y = F.linear(a, w)
+        assert O.rel_l2(got, F.silu(y[:, 0::2]) * y[:, 1::2]) <= TOL
+
+
 GEMV_SHAPES = [(1, 1152, 896), (1, 896, 4864), (2, 4608, 3584), (3, 896, 896), (4, 3584, 18944), (8, 1024, 512),
                (1, 130, 264), (5, 2048, 1024)]
 
