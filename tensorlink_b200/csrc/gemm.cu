@@ -101,7 +101,7 @@ struct GemmCfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (BN == 256) ? 4 : 6;
     static constexpr int TMEM_COLS = 2 * BN;            // two accumulators
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_SMEM_BYTES;
 };
 
 template <int BN, bool A_MN, bool B_MN>
@@ -216,15 +216,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
             mbar_wait(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
-            const int row = m0 + quarter * 32 + lane;
+            const int row0 = m0 + quarter * 32;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+            unsigned char* stg = smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256 + (warp - 2) * EPI_STAGE_BYTES;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld32(taddr + (uint32_t)(c * 32), r);
+            for (int c = 0; c < BN / 64; ++c) {
+                uint32_t r0[32], r1[32];
+                tmem_ld32(taddr + (uint32_t)(c * 64), r0);
+                tmem_ld32(taddr + (uint32_t)(c * 64 + 32), r1);
                 tmem_ld_wait();
-                const int col0 = n0 + c * 32;
-                gemm_epilogue_chunk(r, Cv, row, col0, M, N, ldc, bias, residual, ldr, flags);
+                gemm_epilogue_chunk64(r0, r1, stg, Cv, row0, lane, n0 + c * 64, M, N, ldc, bias, residual, ldr, flags);
             }
             tcgen05_fence_before();
             __syncwarp();

@@ -20,7 +20,7 @@ constexpr int G2_B_BYTES = (G2_BN / 2) * BK * 2; // 16 KB: this CTA's half of B
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
 constexpr int G2_STAGES = 6;
 constexpr int G2_TMEM_COLS = 2 * G2_BN;
-constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + 1024 + 256;
+constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + 1024 + 256 + EPI_SMEM_BYTES;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -179,14 +179,16 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int m0 = (t % tiles_m) * (2 * BM) + (int)cta_rank * BM, n0 = (t / tiles_m) * G2_BN;
             mbar_wait(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
-            const int row = m0 + quarter * 32 + lane;
+            const int row0 = m0 + quarter * 32;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * G2_BN);
+            unsigned char* stg = smem + G2_STAGES * G2_STAGE_BYTES + 256 + (warp - 2) * EPI_STAGE_BYTES;
 #pragma unroll 1
-            for (int c = 0; c < G2_BN / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld32(taddr + (uint32_t)(c * 32), r);
+            for (int c = 0; c < G2_BN / 64; ++c) {
+                uint32_t r0[32], r1[32];
+                tmem_ld32(taddr + (uint32_t)(c * 64), r0);
+                tmem_ld32(taddr + (uint32_t)(c * 64 + 32), r1);
                 tmem_ld_wait();
-                gemm_epilogue_chunk(r, Cv, row, n0 + c * 32, M, N, ldc, bias, residual, ldr, flags);
+                gemm_epilogue_chunk64(r0, r1, stg, Cv, row0, lane, n0 + c * 64, M, N, ldc, bias, residual, ldr, flags);
             }
             tcgen05_fence_before();
             __syncwarp();
