@@ -37,8 +37,10 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&t);
 }
-// torch CPU: silu on a bf16 tensor = fp32 x/(1+exp(-x)) rounded to bf16
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+// torch CPU: silu on a bf16 tensor = fp32 x/(1+exp(-x)) rounded to bf16.  The fp32 value only has to be right to
+// well under a bf16 ulp (2^-9), so the SFU forms are used: the IEEE division + expf pair cost ~200 dependent cycles
+// per element in the GEMM epilogue (ncu, round 1: 181 us vs 64 us for the 4096x9728x896 gate/up tile sweep).
+__device__ __forceinline__ float silu_f(float x) { return x * __frcp_rn(1.0f + __expf(-x)); }
 
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
     uint4 r;
