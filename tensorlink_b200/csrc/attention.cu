@@ -3,6 +3,8 @@
 //    the tcgen05/TMEM version is the planned replacement — attention is 3-6 % of the layer FLOPs at the
 //    BASELINE shapes, the tcgen05 GEMMs in gemm.cu carry the rest).
 //  * decode: one query per batch row, split over the KV length, HBM-bound on the cache read.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace tl {
@@ -440,6 +442,10 @@ __global__ void __launch_bounds__(FD_THREADS) attn_decode_fused_kernel(
     const bf16* __restrict__ q_norm_w, const bf16* __restrict__ k_norm_w, float eps, int n_h, int n_kv, int T_max,
     float scale_log2) {
     constexpr int HALF = D / 2;
+    // programmatic dependent launch: this grid may become resident while the qkv Linear is still running; wait for its
+    // output here, and let the o-proj Linear behind us start prefetching its weights right away
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
     const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_rep = n_h / n_kv, kvh = h / n_rep;
     const int pos = *pos_dev;                       // keys 0..pos-1 are cached; the new token is key `pos`
@@ -594,13 +600,28 @@ extern "C" int tl_attn_decode_fused(const void* qkv, void* k_cache, void* v_cach
     const float sl2 = scale * 1.4426950408889634f;
     const dim3 grid(n_h, B);
     cudaStream_t st = (cudaStream_t)stream;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(FD_THREADS);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static int use_pdl = -1;
+    if (use_pdl < 0) {
+        const char* e = getenv("TL_PDL");
+        use_pdl = (e && e[0] == '0') ? 0 : 1;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = use_pdl ? 1 : 0;
     if (d == 64)
-        attn_decode_fused_kernel<64><<<grid, FD_THREADS, 0, st>>>((const bf16*)qkv, (bf16*)k_cache, (bf16*)v_cache, (bf16*)out,
-                                                                  pos_dev, (const bf16*)cos_tab, (const bf16*)sin_tab,
-                                                                  (const bf16*)q_norm_w, (const bf16*)k_norm_w, eps, n_h, n_kv, T_max, sl2);
+        cudaLaunchKernelEx(&cfg, attn_decode_fused_kernel<64>, (const bf16*)qkv, (bf16*)k_cache, (bf16*)v_cache, (bf16*)out, pos_dev,
+                           (const bf16*)cos_tab, (const bf16*)sin_tab, (const bf16*)q_norm_w, (const bf16*)k_norm_w, eps, n_h, n_kv,
+                           T_max, sl2);
     else
-        attn_decode_fused_kernel<128><<<grid, FD_THREADS, 0, st>>>((const bf16*)qkv, (bf16*)k_cache, (bf16*)v_cache, (bf16*)out,
-                                                                   pos_dev, (const bf16*)cos_tab, (const bf16*)sin_tab,
-                                                                   (const bf16*)q_norm_w, (const bf16*)k_norm_w, eps, n_h, n_kv, T_max, sl2);
+        cudaLaunchKernelEx(&cfg, attn_decode_fused_kernel<128>, (const bf16*)qkv, (bf16*)k_cache, (bf16*)v_cache, (bf16*)out, pos_dev,
+                           (const bf16*)cos_tab, (const bf16*)sin_tab, (const bf16*)q_norm_w, (const bf16*)k_norm_w, eps, n_h, n_kv,
+                           T_max, sl2);
     return check_launch("tl_attn_decode_fused");
 }

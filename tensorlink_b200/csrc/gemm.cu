@@ -314,7 +314,7 @@ extern "C" int tl_gemm_bf16(const void* A, const void* B, void* C, int M, int N,
     cudaStream_t st = (cudaStream_t)stream;
     // 256x256 tiles on CTA pairs (cta_group::2) when there are enough of them to fill the 74 pairs
     const long long tiles2 = (long long)((M + 255) / 256) * ((N + 255) / 256);
-    if (use_2cta() && M > 128 && N >= 256 && tiles2 >= (long long)(sm_count() / 2))
+    if (use_2cta() && M > 128 && N >= 256 && tiles2 * 3 >= (long long)sm_count())     // >= ~2/3 of the 74 pairs busy
         return gemm2_dispatch(a_mn, b_mn, A, B, C, M, N, K, lda, ldb, ldc, bias, residual, flags, st);
     // 128x256 tiles when they still fill the machine, else 128x128
     const long long tiles256 = (long long)((M + BM - 1) / BM) * ((N + 255) / 256);

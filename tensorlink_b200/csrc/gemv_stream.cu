@@ -26,7 +26,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 
 template <int M>
-__global__ void __launch_bounds__(GS_THREADS, 1)
+__global__ void __launch_bounds__(GS_THREADS, 2)
 gemv_stream_kernel(const bf16* __restrict__ x, const bf16* __restrict__ W, bf16* __restrict__ y, int N, int K,
                    const bf16* __restrict__ bias, const bf16* __restrict__ residual, const bf16* __restrict__ norm_w,
                    float eps, int flags, int P, int n_stages, int NW, int stage_bytes) {
@@ -248,10 +248,17 @@ template <int M>
 static int launch_stream(const void* x, const void* W, void* y, int N, int K, const void* bias, const void* residual,
                          const void* norm_w, float eps, int flags, cudaStream_t st) {
     auto kern = gemv_stream_kernel<M>;
-    constexpr int SMEM_CAP = 220 * 1024;
+    // TL_GEMV_CTAS_PER_SM=2: two half-size rings per SM (16 consumer warps, finer work split, and the next kernel's
+    // CTAs can become resident as soon as one of the two exits); 1 = one deep ring per SM
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        const char* e = getenv("TL_GEMV_CTAS_PER_SM");
+        per_sm = (e && e[0] == '2') ? 2 : 1;
+    }
+    const int SMEM_CAP = per_sm == 2 ? 110 * 1024 : 220 * 1024;
     static bool attr_done = false;
     if (!attr_done) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAP) != cudaSuccess)
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
             return check_launch("tl_gemv_bf16/stream (smem attr)");
         attr_done = true;
     }
@@ -274,7 +281,7 @@ static int launch_stream(const void* x, const void* W, void* y, int N, int K, co
     }
     const size_t smem = (size_t)n_stages * stage_bytes + fixed;
     const int npairs = N >> 1;
-    int grid = sm_count();
+    int grid = sm_count() * per_sm;
     if (grid > npairs) grid = npairs;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
