@@ -248,8 +248,8 @@ class DistributedModel(torch.nn.Module):
                         link.wait(sent_x[m])                       # x_dec[m] still feeding the previous hop?
                         link.recv_up(st.ids_dec[m][:b], self.world - 1)
                     out_tokens[m * b:(m + 1) * b, step] = st.ids_dec[m][:b]
-                    if streamer is not None and n_mb == 1:
-                        streamer.put(st.ids_dec[m][:b].cpu())
+                    if streamer is not None and m == n_mb - 1:
+                        streamer.put(out_tokens[:, step].cpu())         # all rows of this step, one column
                 if step == max_new - 1:
                     continue
                 if not link.first:

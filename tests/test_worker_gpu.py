@@ -1,0 +1,60 @@
+"""DistributedWorker mirror (tensorlink/ml/worker.py handler surface) over the CUDA stage."""
+import pytest
+import torch
+
+from tensorlink_b200.ml import configs as C
+from tensorlink_b200.ml.weights import synthetic_tokens
+
+pytestmark = pytest.mark.gpu
+
+
+def test_two_workers_compose_like_one_shard_and_generate():
+    from tensorlink_b200.ml import DistributedModel
+    from tensorlink_b200.ml.worker import DistributedWorker
+    cfg = C.TINY_QWEN2_D128
+    w = DistributedWorker(max_batch=2, max_seq=64)
+    a = w.load_module({"module_id": "a" * 64, "name": cfg.name, "type": "offloaded_group", "layer_range": (0, 1), "training": False})
+    b = w.load_module({"module_id": "b" * 64, "name": cfg.name, "type": "offloaded_group", "layer_range": (2, 3), "training": False})
+    full = w.load_module({"module_id": "f" * 64, "name": cfg.name, "type": "offloaded", "has_embed": True, "has_head": True})
+    ids = synthetic_tokens(cfg, 2, 17).cuda()
+    x0 = w.modules[full].embed(ids)
+    o1 = w._handle_forward(a, (0, 0, a), {"hidden_states": x0, "use_cache": False, "position_ids": None})
+    assert set(o1) == {"hidden_states", "use_cache", "position_ids"}           # kwargs ∪ outputs
+    o2 = w._handle_forward(b, (0, 0, b), o1)
+    ref = w._handle_forward(full, (0, 0, full), {"hidden_states": x0})
+    assert torch.equal(o2["hidden_states"], ref["hidden_states"])              # sharded == unsharded, bit for bit
+
+    class S:
+        def __init__(self):
+            self.cols, self.ended = [], False
+
+        def put(self, t):
+            self.cols.append(t)
+
+        def end(self):
+            self.ended = True
+    s = S()
+    got = w._handle_generate(full, ids, max_new_tokens=10, stream=s)
+    want = DistributedModel(cfg, training=False, max_batch=2, max_seq=64).generate(ids, max_new_tokens=10)
+    assert torch.equal(got, want)
+    assert s.ended and torch.equal(torch.stack(s.cols, 1).cuda(), got[:, 17:])
+
+
+def test_worker_training_ops():
+    from tensorlink_b200.ml.worker import DistributedWorker
+    cfg = C.TINY_QWEN2
+    w = DistributedWorker(max_batch=2, max_seq=32)
+    mid = w.load_module({"module_id": "t" * 64, "name": cfg.name, "type": "offloaded_group", "layer_range": (0, 3),
+                         "training": True, "optimizer_type": "adam"})
+    assert w.process_state_update(mid, ("init", {"lr": 1e-2})) == "loaded"
+    assert w.process_state_update(mid, ("zero_grad", None)) == "zeroed"
+    x = (torch.randn(2, 16, cfg.hidden, device="cuda") * 0.05).bfloat16()
+    key = (0, 0, mid)
+    y = w._handle_forward(mid, key, {"hidden_states": x})["hidden_states"]
+    dx = w._handle_backward(mid, key, torch.randn_like(y) * 0.01)
+    assert dx.shape == x.shape and torch.isfinite(dx.float()).all() and float(dx.float().abs().sum()) > 0
+    before = w.modules[mid].params.flat.clone()
+    assert w.process_state_update(mid, ("step", None)) == "stepped"
+    assert float((w.modules[mid].params.flat.float() - before.float()).abs().sum()) > 0
+    with pytest.raises(KeyError):
+        w._handle_backward(mid, key, torch.randn_like(y))                      # intermediates are consumed once
