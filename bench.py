@@ -262,6 +262,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="qwen2.5-7b", choices=sorted(WORKLOADS))
     ap.add_argument("--rows-per-gpu", type=int, default=1)
+    ap.add_argument("--prompt", type=int, default=0, help="override the workload's prompt length")
+    ap.add_argument("--new", type=int, default=0, help="override the workload's number of generated tokens")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step measurement")
@@ -270,6 +272,7 @@ def main():
     ap.add_argument("--train-seq", type=int, default=512)
     args = ap.parse_args()
     name, prompt, new = WORKLOADS[args.workload]
+    prompt, new = args.prompt or prompt, args.new or new
     # exactly ONE line goes to stdout: NCCL / torch banners printed during start-up are diverted to stderr
     real_stdout = os.dup(1)
     os.dup2(2, 1)

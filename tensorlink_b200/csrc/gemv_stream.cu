@@ -26,7 +26,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 
 template <int M>
-__global__ void __launch_bounds__(GS_THREADS, 2)
+__global__ void __launch_bounds__(GS_THREADS, 1)
 gemv_stream_kernel(const bf16* __restrict__ x, const bf16* __restrict__ W, bf16* __restrict__ y, int N, int K,
                    const bf16* __restrict__ bias, const bf16* __restrict__ residual, const bf16* __restrict__ norm_w,
                    float eps, int flags, int P, int n_stages, int NW, int stage_bytes) {
