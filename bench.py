@@ -162,10 +162,16 @@ def measure_gemv_launches(dm, rows):
     for rep in range(3):
         evs = []
         for li in grp.layer_ids:
-            calls = (("qkv", lambda: nat.gemv(x, v[f"l{li}.wqkv"], out=w.qkv, bias=v.get(f"l{li}.bqkv"), norm_w=v[f"l{li}.ln1"], eps=cfg.rms_eps)),
-                     ("o", lambda: nat.gemv(w.attn, v[f"l{li}.wo"], out=x, residual=x)),
-                     ("gate_up", lambda: nat.gemv(x, v[f"l{li}.wgu"], out=w.act, norm_w=v[f"l{li}.ln2"], eps=cfg.rms_eps, flags=nat.EPI_SWIGLU)),
-                     ("down", lambda: nat.gemv(w.act, v[f"l{li}.wd"], out=x, residual=x)))
+            if rows <= 4:
+                calls = (("qkv", lambda: nat.gemv(x, v[f"l{li}.wqkv"], out=w.qkv, bias=v.get(f"l{li}.bqkv"), norm_w=v[f"l{li}.ln1"], eps=cfg.rms_eps)),
+                         ("o", lambda: nat.gemv(w.attn, v[f"l{li}.wo"], out=x, residual=x)),
+                         ("gate_up", lambda: nat.gemv(x, v[f"l{li}.wgu"], out=w.act, norm_w=v[f"l{li}.ln2"], eps=cfg.rms_eps, flags=nat.EPI_SWIGLU)),
+                         ("down", lambda: nat.gemv(w.act, v[f"l{li}.wd"], out=x, residual=x)))
+            else:       # batched decode streams the weights through the tcgen05 GEMM (M = rows)
+                calls = (("qkv", lambda: nat.gemm(x, v[f"l{li}.wqkv"], out=w.qkv, bias=v.get(f"l{li}.bqkv"))),
+                         ("o", lambda: nat.gemm(w.attn, v[f"l{li}.wo"], out=x, residual=x)),
+                         ("gate_up", lambda: nat.gemm(x, v[f"l{li}.wgu"], out=w.act, flags=nat.EPI_SWIGLU)),
+                         ("down", lambda: nat.gemm(w.act, v[f"l{li}.wd"], out=x, residual=x)))
             for name, fn in calls:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(); fn(); e1.record()
@@ -192,7 +198,8 @@ def measure_training(args, N, rank, world, tf_peak, peak_kind):
     from tensorlink_b200.ml.weights import synthetic_tokens
     cfg = get_config(args.train_model)
     B, S = args.train_batch * N, args.train_seq
-    dm = DistributedModel(args.train_model, training=True, n_pipelines=N, max_batch=B, max_seq=S, init="device",
+    n_mb = N if N == 1 else 2 * N           # more micro-batches than stages: pipeline bubble (N-1)/(n_mb+N-1)
+    dm = DistributedModel(args.train_model, training=True, n_pipelines=n_mb, max_batch=B, max_seq=S, init="device",
                           optimizer=torch.optim.Adam, max_tokens=8, balanced_plan=N > 1)
     opt = dm.create_optimizer(lr=1e-4)
     ids_host = synthetic_tokens(cfg, B, S).pin_memory()
@@ -244,7 +251,7 @@ def measure_training(args, N, rank, world, tf_peak, peak_kind):
     ach = 2.0 * M * Nn * K / tg / 1e12
     res = {"metric": "training samples/sec", "value": B * args.steps / t, "unit": "samples/s", "ms_per_step": t / args.steps * 1e3,
            "loss": float(loss.detach()), "config": {"workload": f"{args.train_model} bf16, one optimizer step (fwd + bwd + Adam), "
-                                                       f"global batch {B} x seq {S}, {N} micro-batch(es), {N} stage(s)",
+                                                       f"global batch {B} x seq {S}, {n_mb} micro-batch(es), {N} stage(s), all-forward-then-all-backward schedule",
                                            "h2d_bytes_per_step": B * S * 8, "d2h_bytes_per_step": 4},
            "model_tflops_per_s": flops * args.steps / t / 1e12, "gpu_launches": tr.launches - l0,
            "roofline": {"bound": "tensor", "kernel": "tl::gemm_bf16_kernel (gate/up forward GEMM)", "achieved": ach,
@@ -364,6 +371,14 @@ def main():
     sync_all()
     t_e2e = torch.tensor([max(e2.elapsed_time(e3) * 1e-3, time.perf_counter() - t0)], device=dm.device)
     clocks = sampler.stop() if rank == 0 else None
+    # ---- pipeline occupancy: fraction of the decode phase this rank's compute stream spent inside decode launches
+    # (the rest = waiting for a neighbour's activations / ids, i.e. exposed transfer + pipeline bubble)
+    dm.generate(ids_dev, max_new_tokens=new, profile=True)
+    busy = torch.tensor([dm.timers["decode_busy_s"] / max(dm.timers["decode_span_s"], 1e-9)], device=dm.device)
+    busy_min, busy_max = busy.clone(), busy.clone()
+    if world > 1:
+        dist.all_reduce(busy_min, op=dist.ReduceOp.MIN)
+        dist.all_reduce(busy_max, op=dist.ReduceOp.MAX)
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
@@ -378,7 +393,8 @@ def main():
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get(f"gemv_gate_up:{name}")
-    roof = {"bound": "hbm", "kernel": "tl::gemv_kernel (gate/up instantiation, SwiGLU epilogue)",
+    roof = {"bound": "hbm", "kernel": ("tl::gemv_stream_kernel (gate/up Linear, RMSNorm prologue + SwiGLU epilogue)" if args.rows_per_gpu <= 4
+                                       else "tl::gemm_bf16_kernel (gate/up Linear at M = rows, weight-streaming regime)"),
             "achieved": gv["gate_up"]["GBps"], "peak": hbm_peak, "peak_kind": f"{peak_kind} copy bandwidth (burst)",
             "unit": "GB/s", "frac": gv["gate_up"]["GBps"] / hbm_peak, "traffic": traffic,
             "algorithmic_bytes_per_launch": gv["gate_up"]["bytes"], "launch_s": gv["gate_up"]["s"],
@@ -395,7 +411,13 @@ def main():
     line = dict(base, value=toks / t_dev, ms_per_step=t_dev / args.steps * 1e3,
                 e2e={"value": toks / t_e2e, "unit": "tokens/s", "h2d_bytes_per_step": rows * prompt * 8,
                      "d2h_bytes_per_step": rows * (prompt + new) * 8},
-                gpu_launches=launches, clocks=clocks, roofline=roof)
+                gpu_launches=launches, clocks=clocks, roofline=roof,
+                pipeline={"stages": N, "micro_batches": N, "decode_busy_frac_min_over_ranks": float(busy_min),
+                          "decode_busy_frac_max_over_ranks": float(busy_max),
+                          "exposed_wait_frac_worst_rank": 1.0 - float(busy_min),
+                          "hop_bytes_per_token_step": args.rows_per_gpu * cfg.hidden * 2,
+                          "note": "CUDA events around every decode launch vs the whole decode phase, per rank; at N=1 the "
+                                  "remainder is host launch gaps only"})
     if not args.no_train:
         del dm
         torch.cuda.empty_cache()

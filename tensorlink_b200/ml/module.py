@@ -205,6 +205,7 @@ class DistributedModel(torch.nn.Module):
         max_new = int(kwargs.pop("max_new_tokens", 20))
         streamer = kwargs.pop("streamer", None)
         use_graph = kwargs.pop("use_graph", True)
+        profile = kwargs.pop("profile", False)       # CUDA events around every decode launch -> self.timers["decode_busy_s"]
         if kwargs.pop("do_sample", False):
             raise NotImplementedError("sampling is not implemented; generate() is greedy (do_sample=False)")
         kwargs.pop("eos_token_id", None); kwargs.pop("pad_token_id", None)
@@ -241,6 +242,10 @@ class DistributedModel(torch.nn.Module):
         # Sends are asynchronous; a slot's buffer is waited on only right before the next step overwrites it.
         sent_x = [None] * n_mb
         sent_ids = [None] * n_mb
+        prof_events = []
+        if profile:
+            span = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            span[0].record()
         for step in range(max_new):
             for m in range(n_mb):
                 if link.first:
@@ -257,12 +262,23 @@ class DistributedModel(torch.nn.Module):
                     link.recv_prev(st.x_dec[m][:b])
                 if link.last and multi:
                     link.wait(sent_ids[m])
+                if profile:
+                    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                    ev[0].record()
                 st.decode(m, b, use_graph)
+                if profile:
+                    ev[1].record()
+                    prof_events.append(ev)
                 if not link.last:
                     sent_x[m] = link.send_next(st.x_dec[m][:b])
                 elif multi:
                     sent_ids[m] = link.send_up(st.ids_dec[m][:b], 0)
         link.flush()
+        if profile:
+            span[1].record()
+            torch.cuda.synchronize()
+            self.timers["decode_span_s"] = span[0].elapsed_time(span[1]) * 1e-3
+            self.timers["decode_busy_s"] = sum(a.elapsed_time(b_) for a, b_ in prof_events) * 1e-3
         if link.first:
             result = torch.cat([input_ids.to(dev), out_tokens], dim=1)
         else:
