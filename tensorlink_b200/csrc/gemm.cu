@@ -318,7 +318,9 @@ extern "C" int tl_gemm_bf16(const void* A, const void* B, void* C, int M, int N,
         return gemm2_dispatch(a_mn, b_mn, A, B, C, M, N, K, lda, ldb, ldc, bias, residual, flags, st);
     // 128x256 tiles when they still fill the machine, else 128x128
     const long long tiles256 = (long long)((M + BM - 1) / BM) * ((N + 255) / 256);
-    const bool use256 = (N >= 256) && tiles256 >= (long long)sm_count();
+    // single-M-tile problems (batched decode, M <= 128) are weight-streaming: prefer >= 2 tiles per CTA so the
+    // pipeline fill / epilogue of one tile overlaps the stream of the next
+    const bool use256 = (N >= 256) && tiles256 >= (long long)sm_count() * (M <= BM ? 2 : 1);
     if (use256) return dispatch_major<256>(a_mn, b_mn, A, B, C, M, N, K, lda, ldb, ldc, bias, residual, flags, st);
     return dispatch_major<128>(a_mn, b_mn, A, B, C, M, N, K, lda, ldb, ldc, bias, residual, flags, st);
 }
