@@ -611,7 +611,8 @@ extern "C" int tl_attn_decode_fused(const void* qkv, void* k_cache, void* v_cach
     static int use_pdl = -1;
     if (use_pdl < 0) {
         const char* e = getenv("TL_PDL");
-        use_pdl = (e && e[0] == '0') ? 0 : 1;
+        const char* e2 = getenv("TL_PDL_ATTN");
+        use_pdl = ((e && e[0] == '0') || (e2 && e2[0] == '0')) ? 0 : 1;
     }
     cfg.attrs = attr;
     cfg.numAttrs = use_pdl ? 1 : 0;

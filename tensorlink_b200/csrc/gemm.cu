@@ -99,8 +99,8 @@ struct GemmCfg {
     static constexpr int A_BYTES = BM * BK * 2;         // 16 KB
     static constexpr int B_BYTES = BN * BK * 2;         // 16 / 32 KB
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 4 : 6;
-    static constexpr int TMEM_COLS = 2 * BN;            // two accumulators
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 9);
+    static constexpr int TMEM_COLS = 2 * BN;            // two accumulators (>= 32 columns, power of two)
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_SMEM_BYTES;
 };
 
@@ -219,13 +219,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int row0 = m0 + quarter * 32;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
             unsigned char* stg = smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256 + (warp - 2) * EPI_STAGE_BYTES;
+            if (BN >= 64) {
 #pragma unroll 1
-            for (int c = 0; c < BN / 64; ++c) {
+                for (int c = 0; c < BN / 64; ++c) {
+                    uint32_t r0[32], r1[32];
+                    tmem_ld32(taddr + (uint32_t)(c * 64), r0);
+                    tmem_ld32(taddr + (uint32_t)(c * 64 + 32), r1);
+                    tmem_ld_wait();
+                    gemm_epilogue_chunk64(r0, r1, stg, Cv, row0, lane, n0 + c * 64, M, N, ldc, bias, residual, ldr, flags);
+                }
+            } else {      // 32-wide tile: one half chunk
                 uint32_t r0[32], r1[32];
-                tmem_ld32(taddr + (uint32_t)(c * 64), r0);
-                tmem_ld32(taddr + (uint32_t)(c * 64 + 32), r1);
+                tmem_ld32(taddr, r0);
                 tmem_ld_wait();
-                gemm_epilogue_chunk64(r0, r1, stg, Cv, row0, lane, n0 + c * 64, M, N, ldc, bias, residual, ldr, flags);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r1[j] = 0u;
+                gemm_epilogue_chunk64(r0, r1, stg, Cv, row0, lane, n0, M, N, ldc, bias, residual, ldr, flags, 32);
             }
             tcgen05_fence_before();
             __syncwarp();
@@ -321,6 +330,9 @@ extern "C" int tl_gemm_bf16(const void* A, const void* B, void* C, int M, int N,
     // single-M-tile problems (batched decode, M <= 128) are weight-streaming: prefer >= 2 tiles per CTA so the
     // pipeline fill / epilogue of one tile overlaps the stream of the next
     const bool use256 = (N >= 256) && tiles256 >= (long long)sm_count() * (M <= BM ? 2 : 1);
+    // few rows (M <= 128) and not enough 128-wide tiles to occupy every SM: 32-wide tiles (weight streaming)
+    if (M <= BM && !b_mn && (long long)((N + 127) / 128) < 2LL * sm_count() && N % 32 == 0)
+        return dispatch_major<32>(a_mn, b_mn, A, B, C, M, N, K, lda, ldb, ldc, bias, residual, flags, st);
     if (use256) return dispatch_major<256>(a_mn, b_mn, A, B, C, M, N, K, lda, ldb, ldc, bias, residual, flags, st);
     return dispatch_major<128>(a_mn, b_mn, A, B, C, M, N, K, lda, ldb, ldc, bias, residual, flags, st);
 }

@@ -70,9 +70,9 @@ __device__ __forceinline__ void epi_store_tile(const unsigned char* stg, unsigne
 __device__ __forceinline__ void gemm_epilogue_chunk64(const uint32_t (&r0)[32], const uint32_t (&r1)[32], unsigned char* stg,
                                                       void* Cv, int row0, int lane, int col0, int M, int N, int ldc,
                                                       const bf16* __restrict__ bias, const bf16* __restrict__ residual,
-                                                      int ldr, int flags) {
+                                                      int ldr, int flags, int max_cols = 64) {
     if (row0 >= M || col0 >= N) return;                 // warp-uniform
-    const int ncols = min(64, N - col0);                // multiple of 8
+    const int ncols = min(max_cols, N - col0);          // multiple of 8 (max_cols = 32 for 32-wide tiles)
     float v[64];
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -114,7 +114,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk64(const uint32_t (&r0)[32], 
 #pragma unroll
         for (int hb = 0; hb < 2; ++hb) {
             const int c0 = col0 + hb * 32;
-            if (c0 >= N) break;
+            if (c0 >= N || hb * 32 >= max_cols) break;
             const int vb = min(32, N - c0) * 4;
             unsigned char* g = reinterpret_cast<unsigned char*>(Cv) + ((size_t)row0 * ldc + c0) * 4;
             if (flags & TL_EPI_ACCUM) {

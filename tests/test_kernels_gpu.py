@@ -149,6 +149,18 @@ def test_gemm_2cta_tiles(nat, M, N, K):
         assert O.rel_l2(got, F.silu(y[:, 0::2]) * y[:, 1::2]) <= TOL
 
 
+@pytest.mark.parametrize("M,N,K", [(32, 3584, 18944), (9, 4608, 3584), (100, 896, 4864), (32, 2048, 512)])
+def test_gemm_small_m_streaming_tiles(nat, M, N, K):
+    """batched-decode shapes (M <= 128, few column tiles): 32-wide tiles so every SM streams weights"""
+    a, w, b, r = rnd(M, K, seed=36), rnd(N, K, seed=37, std=0.05), rnd(N, seed=38, std=0.5), rnd(M, N, seed=39)
+    assert O.rel_l2(nat.gemm(dev(a), dev(w), bias=dev(b), residual=dev(r)).cpu(), r + F.linear(a, w, b)) <= TOL
+    got = nat.gemm(dev(a), dev(w), flags=nat.EPI_OUT_F32).cpu()
+    assert O.rel_l2(got, a.double() @ w.double().t()) <= 1e-5
+    if N % 16 == 0:
+        y = F.linear(a, w)
+        assert O.rel_l2(nat.gemm(dev(a), dev(w), flags=nat.EPI_SWIGLU).cpu(), F.silu(y[:, 0::2]) * y[:, 1::2]) <= TOL
+
+
 GEMV_SHAPES = [(1, 1152, 896), (1, 896, 4864), (2, 4608, 3584), (3, 896, 896), (4, 3584, 18944), (8, 1024, 512),
                (1, 130, 264), (5, 2048, 1024)]
 
