@@ -66,6 +66,12 @@ int tl_embed_fwd(const int64_t* ids, const void* table, void* out, int n_tokens,
 int tl_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
                  const void* bias, const void* residual, int flags, void* stream);
 
+/* same contract with a caller-provided workspace (>= tl_gemm_splitk_ws(M, N) bytes): batched-decode shapes (M <= 128) whose
+ * few output tiles cannot occupy every SM are split along K (fp32 partials + one reduce/epilogue pass) */
+size_t tl_gemm_splitk_ws(int M, int N);
+int tl_gemm_bf16_ws(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
+                    const void* bias, const void* residual, int flags, void* workspace, size_t ws_bytes, void* stream);
+
 /* ---- decode-shaped Linear (M <= 8 tokens), HBM-bound weight streaming:
  * y[M,N] = f(norm(x)[M,K] * W[N,K]^T).  norm_w != NULL fuses the preceding RMSNorm (K1) as a prologue. */
 int tl_gemv_bf16(const void* x, const void* W, void* y, int M, int N, int K, const void* bias,

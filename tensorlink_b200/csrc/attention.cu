@@ -612,7 +612,9 @@ extern "C" int tl_attn_decode_fused(const void* qkv, void* k_cache, void* v_cach
     if (use_pdl < 0) {
         const char* e = getenv("TL_PDL");
         const char* e2 = getenv("TL_PDL_ATTN");
-        use_pdl = ((e && e[0] == '0') || (e2 && e2[0] == '0')) ? 0 : 1;
+        // measured (round 1, Qwen2.5-7B B=1): an early-resident attention grid costs more than it hides (329 vs 349 tok/s),
+        // so the attribute is opt-in here (TL_PDL_ATTN=1); the weight-streaming Linears keep it on by default
+        use_pdl = (!(e && e[0] == '0') && (e2 && e2[0] == '1')) ? 1 : 0;
     }
     cfg.attrs = attr;
     cfg.numAttrs = use_pdl ? 1 : 0;

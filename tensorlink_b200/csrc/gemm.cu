@@ -108,7 +108,7 @@ template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, void* __restrict__ Cv,
                  int M, int N, int K, int ldc, const bf16* __restrict__ bias, const bf16* __restrict__ residual,
-                 int ldr, int flags) {
+                 int ldr, int flags, int k_splits, int kb_per) {
     using Cfg = GemmCfg<BN>;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -121,7 +121,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
-    const int total_tiles = tiles_m * tiles_n;
+    // split-K (weight-streaming regime, few output tiles): work item = (tile, k range); partial sums go to an fp32
+    // workspace Cv[split][M][N] and a small reduce kernel applies the epilogue
+    const int mn_tiles = tiles_m * tiles_n;
+    const int total_tiles = mn_tiles * k_splits;
     const int num_k = (K + BK - 1) / BK;
 
     if (warp == 0 && lane == 0) {
@@ -149,8 +152,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
-                for (int kb = 0; kb < num_k; ++kb) {
+                const int ks = t / mn_tiles, tt = t - ks * mn_tiles;
+                const int m0 = (tt % tiles_m) * BM, n0 = (tt / tiles_m) * BN;
+                const int kb0 = ks * kb_per, kb1 = min(num_k, kb0 + kb_per);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     unsigned char* sa = smem + stage * Cfg::STAGE_BYTES;
                     unsigned char* sb = sa + Cfg::A_BYTES;
@@ -185,7 +190,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                for (int kb = 0; kb < num_k; ++kb) {
+                const int ks = t / mn_tiles;
+                const int kb0 = ks * kb_per, kb1 = min(num_k, kb0 + kb_per);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tcgen05_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -198,10 +205,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     for (int k = 0; k < BK / 16; ++k) {
                         const uint64_t ak = da + (uint64_t)((A_MN ? 2048 : 32) * k >> 4);
                         const uint64_t bk = db + (uint64_t)((B_MN ? 2048 : 32) * k >> 4);
-                        umma_bf16(d_tmem, ak, bk, idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_bf16(d_tmem, ak, bk, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
-                    if (kb == num_k - 1) umma_commit(&tmem_full[acc]);
+                    if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -213,7 +220,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
+            const int ks = t / mn_tiles, tt = t - ks * mn_tiles;
+            const int m0 = (tt % tiles_m) * BM, n0 = (tt / tiles_m) * BN;
+            void* Ct = k_splits > 1 ? (void*)(reinterpret_cast<float*>(Cv) + (size_t)ks * M * N) : Cv;
             mbar_wait(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
             const int row0 = m0 + quarter * 32;
@@ -226,7 +235,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     tmem_ld32(taddr + (uint32_t)(c * 64), r0);
                     tmem_ld32(taddr + (uint32_t)(c * 64 + 32), r1);
                     tmem_ld_wait();
-                    gemm_epilogue_chunk64(r0, r1, stg, Cv, row0, lane, n0 + c * 64, M, N, ldc, bias, residual, ldr, flags);
+                    gemm_epilogue_chunk64(r0, r1, stg, Ct, row0, lane, n0 + c * 64, M, N, ldc, bias, residual, ldr, flags);
                 }
             } else {      // 32-wide tile: one half chunk
                 uint32_t r0[32], r1[32];
@@ -234,7 +243,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; ++j) r1[j] = 0u;
-                gemm_epilogue_chunk64(r0, r1, stg, Cv, row0, lane, n0, M, N, ldc, bias, residual, ldr, flags, 32);
+                gemm_epilogue_chunk64(r0, r1, stg, Ct, row0, lane, n0, M, N, ldc, bias, residual, ldr, flags, 32);
             }
             tcgen05_fence_before();
             __syncwarp();
@@ -252,7 +261,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 template <int BN, bool A_MN, bool B_MN>
 static int launch_gemm(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
-                       const void* bias, const void* residual, int flags, cudaStream_t st) {
+                       const void* bias, const void* residual, int flags, cudaStream_t st, int k_splits = 1, int kb_per = 0) {
     using Cfg = GemmCfg<BN>;
     CUtensorMap tmA, tmB;
     int rc;
@@ -271,11 +280,12 @@ static int launch_gemm(const void* A, const void* B, void* C, int M, int N, int 
             return check_launch("tl_gemm_bf16 (smem attr)");
         attr_done = true;
     }
-    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * k_splits;
     const int grid = tiles < sm_count() ? tiles : sm_count();
     const int ldr = ldc;
+    if (kb_per <= 0) kb_per = (K + BK - 1) / BK;
     kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, C, M, N, K, ldc, (const bf16*)bias,
-                                                      (const bf16*)residual, ldr, flags);
+                                                      (const bf16*)residual, ldr, flags, k_splits, kb_per);
     return check_launch("tl_gemm_bf16");
 }
 
@@ -286,6 +296,48 @@ static int dispatch_major(bool a_mn, bool b_mn, const void* A, const void* B, vo
     if (!a_mn && b_mn) return launch_gemm<BN, false, true>(A, B, C, M, N, K, lda, ldb, ldc, bias, residual, flags, st);
     if (a_mn && !b_mn) return launch_gemm<BN, true, false>(A, B, C, M, N, K, lda, ldb, ldc, bias, residual, flags, st);
     return launch_gemm<BN, true, true>(A, B, C, M, N, K, lda, ldb, ldc, bias, residual, flags, st);
+}
+
+// out = epilogue(sum_s ws[s][m][n]); one thread per 8 columns (4 outputs for SwiGLU)
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, void* __restrict__ Cv, int M, int N, int ldc, int splits,
+                                     const bf16* __restrict__ bias, const bf16* __restrict__ residual, int ldr, int flags) {
+    const int groups = N >> 3;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)M * groups) return;
+    const int m = (int)(idx / groups), c0 = (int)(idx - (long long)m * groups) * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    for (int s = 0; s < splits; ++s) {
+        const float4* p = reinterpret_cast<const float4*>(ws + ((size_t)s * M + m) * N + c0);
+        const float4 a = p[0], b = p[1];
+        v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    if (flags & TL_EPI_BIAS) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += bf2f(bias[c0 + j]);
+    }
+    if (flags & TL_EPI_SWIGLU) {
+        bf16* dst = reinterpret_cast<bf16*>(Cv) + (size_t)m * ldc + (c0 >> 1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[j] = f2bf(rbf(silu_f(rbf(v[2 * j]))) * rbf(v[2 * j + 1]));
+        return;
+    }
+    if (flags & TL_EPI_OUT_F32) {
+        float* dst = reinterpret_cast<float*>(Cv) + (size_t)m * ldc + c0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j] = v[j] + ((flags & TL_EPI_ACCUM) ? dst[j] : 0.f);
+        return;
+    }
+    bf16* dst = reinterpret_cast<bf16*>(Cv) + (size_t)m * ldc + c0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float t = rbf(v[j]);
+        if (flags & TL_EPI_RESIDUAL) t += bf2f(residual[(size_t)m * ldr + c0 + j]);
+        if (flags & TL_EPI_ACCUM) t += bf2f(dst[j]);
+        v[j] = t;
+    }
+    *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
 }
 
 int gemm2_dispatch(bool a_mn, bool b_mn, const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
@@ -301,6 +353,40 @@ static bool use_2cta() {
 }
 
 }  // namespace tl
+
+extern "C" size_t tl_gemm_splitk_ws(int M, int N) { return (size_t)8 * (size_t)(M > 128 ? 0 : M) * (size_t)N * sizeof(float); }
+
+extern "C" int tl_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
+                            const void* bias, const void* residual, int flags, void* stream);
+
+// Same as tl_gemm_bf16; with a workspace the weight-streaming regime (M <= 128, K-major operands, too few output tiles to
+// occupy every SM) is split along K so that all SMs stream weights, then reduced with the epilogue applied once.
+extern "C" int tl_gemm_bf16_ws(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
+                               const void* bias, const void* residual, int flags, void* workspace, size_t ws_bytes, void* stream) {
+    using namespace tl;
+    const int tiles_n = (N + 127) / 128, num_k = (K + BK - 1) / BK;
+    const bool plain = !(flags & (TL_A_MN_MAJOR | TL_B_MN_MAJOR));
+    if (workspace && plain && M > 0 && M <= BM && K % 8 == 0 && N % 8 == 0 && tiles_n * 2 <= sm_count() && num_k >= 16) {
+        int splits = sm_count() / tiles_n;
+        if (splits > 8) splits = 8;
+        int kb_per = (num_k + splits - 1) / splits;
+        if (kb_per < 8) kb_per = 8;
+        splits = (num_k + kb_per - 1) / kb_per;
+        if (splits > 1 && ws_bytes >= (size_t)splits * M * N * sizeof(float)) {
+            TL_REQUIRE(!(flags & TL_EPI_BIAS) || bias, TL_ERR_INVALID, "tl_gemm_bf16_ws: BIAS flag without bias pointer");
+            TL_REQUIRE(!(flags & TL_EPI_RESIDUAL) || residual, TL_ERR_INVALID, "tl_gemm_bf16_ws: RESIDUAL flag without pointer");
+            cudaStream_t st = (cudaStream_t)stream;
+            int rc = launch_gemm<128, false, false>(A, B, workspace, M, N, K, lda, ldb, N, nullptr, nullptr, TL_EPI_OUT_F32, st,
+                                                    splits, kb_per);
+            if (rc != TL_OK) return rc;
+            const long long items = (long long)M * (N >> 3);
+            splitk_reduce_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>((const float*)workspace, C, M, N, ldc, splits,
+                                                                                  (const bf16*)bias, (const bf16*)residual, ldc, flags);
+            return check_launch("tl_gemm_bf16_ws (reduce)");
+        }
+    }
+    return tl_gemm_bf16(A, B, C, M, N, K, lda, ldb, ldc, bias, residual, flags, stream);
+}
 
 extern "C" int tl_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
                             const void* bias, const void* residual, int flags, void* stream) {

@@ -200,6 +200,9 @@ class CudaLayerGroup:
         self.n_max = max_tokens or max_batch * max_seq
         self._alloc_bufs(min(self.n_max, 8))
         self.dbufs = self._make_bufs(max_batch)       # decode-time buffers: fixed addresses (captured graphs, job lists)
+        # split-K workspace for batched decode (8 < B <= 128): the qkv / o / down Linears have too few output tiles
+        self.gemm_ws = (torch.empty(nat.gemm_splitk_ws(min(max_batch, 128), max(cfg.qkv_dim, cfg.hidden)), dtype=torch.uint8,
+                                    device=dev) if max_batch > 8 else None)
         self.dec_ws = torch.empty(max(nat.attn_decode_ws(max_batch, cfg.n_heads, cfg.head_dim, max_seq), 16),
                                   dtype=torch.uint8, device=dev)
         self.scale = cfg.head_dim ** -0.5
@@ -272,15 +275,17 @@ class CudaLayerGroup:
         nat.gemv(w.act, v[f"l{li}.wd"], out=x, residual=x)
 
     def _layer_decode_batched(self, j: int, x: torch.Tensor, B: int, w: ShardBuffers):
-        """B > 8 single-token rows: tcgen05 GEMMs (weights streamed once per step) + split-KV decode attention."""
+        """B > 8 single-token rows: tcgen05 GEMMs in the weight-streaming regime (split along K where a Linear has too
+        few output tiles to occupy every SM) + decode attention."""
         cfg, v, li = self.cfg, self.p.v, self.layer_ids[j]
+        ws = self.gemm_ws if B <= 128 else None
         nat.rmsnorm_fwd(x, v[f"l{li}.ln1"], cfg.rms_eps, out=w.h)
-        nat.gemm(w.h, v[f"l{li}.wqkv"], out=w.qkv, bias=v.get(f"l{li}.bqkv"))
+        nat.gemm(w.h, v[f"l{li}.wqkv"], out=w.qkv, bias=v.get(f"l{li}.bqkv"), ws=ws)
         self._decode_attention(j, li, B, w)
-        nat.gemm(w.attn, v[f"l{li}.wo"], out=x, residual=x)
+        nat.gemm(w.attn, v[f"l{li}.wo"], out=x, residual=x, ws=ws)
         nat.rmsnorm_fwd(x, v[f"l{li}.ln2"], cfg.rms_eps, out=w.h)
-        nat.gemm(w.h, v[f"l{li}.wgu"], out=w.act, flags=nat.EPI_SWIGLU)
-        nat.gemm(w.act, v[f"l{li}.wd"], out=x, residual=x)
+        nat.gemm(w.h, v[f"l{li}.wgu"], out=w.act, flags=nat.EPI_SWIGLU, ws=ws)
+        nat.gemm(w.act, v[f"l{li}.wd"], out=x, residual=x, ws=ws)
 
     # ------------------------------------------------------------------------------------------ shard passes
     def prefill(self, hidden: torch.Tensor, past_len: int = 0) -> torch.Tensor:

@@ -30,6 +30,9 @@ _SIGS = {
     "tl_embed_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "tl_gemm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                              c_void_p, c_void_p, c_int, c_void_p]),
+    "tl_gemm_splitk_ws": (c_size_t, [c_int, c_int]),
+    "tl_gemm_bf16_ws": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "tl_gemv_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                              c_float, c_int, c_void_p]),
     "tl_rope_table": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
@@ -170,8 +173,13 @@ def embed_fwd(ids: torch.Tensor, table: torch.Tensor, out: Optional[torch.Tensor
     return out
 
 
+def gemm_splitk_ws(M: int, N: int) -> int:
+    return int(load().tl_gemm_splitk_ws(M, N))
+
+
 def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *, bias=None, residual=None,
-         flags: int = 0, M: Optional[int] = None, N: Optional[int] = None, K: Optional[int] = None) -> torch.Tensor:
+         flags: int = 0, M: Optional[int] = None, N: Optional[int] = None, K: Optional[int] = None,
+         ws: Optional[torch.Tensor] = None) -> torch.Tensor:
     """C[M,N] = A·B^T with the epilogue ``flags``.  A is [M,K] (or [K,M] with A_MN_MAJOR), B is [N,K] (or [K,N])."""
     require_device()
     _bf16(a, b, bias, residual)
@@ -189,6 +197,11 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
         flags |= EPI_BIAS
     if residual is not None:
         flags |= EPI_RESIDUAL
+    if ws is not None:
+        _check(load().tl_gemm_bf16_ws(_p(a), _p(b), _p(out), M, N, K, a.stride(0), b.stride(0), out.stride(0), _p(bias),
+                                      _p(residual), flags, _p(ws), ws.numel() * ws.element_size(), _stream()),
+               "tl_gemm_bf16_ws")
+        return out
     _check(load().tl_gemm_bf16(_p(a), _p(b), _p(out), M, N, K, a.stride(0), b.stride(0), out.stride(0), _p(bias),
                                _p(residual), flags, _stream()), "tl_gemm_bf16")
     return out
