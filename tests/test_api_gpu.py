@@ -1,0 +1,74 @@
+"""API-surface behaviour of the drop-in front end: HF module in, state dict out, edge cases, loud errors."""
+import pytest
+import torch
+
+from oracle import shard_oracle as O
+from tensorlink_b200.ml import configs as C
+from tensorlink_b200.ml.weights import init_state_dict, synthetic_tokens
+from tests.hf_util import hf_model
+
+pytestmark = pytest.mark.gpu
+
+
+def test_hf_module_in_state_dict_out():
+    """DistributedModel(model=<HF nn.Module>) (module.py:251-265 accepts a module): weights are taken from the module;
+    state_dict() returns them under HF names, bit for bit, and an HF model loaded from it reproduces the logits."""
+    from tensorlink_b200.ml import DistributedModel
+    for cfg in (C.TINY_QWEN2, C.TINY_QWEN3):
+        sd = init_state_dict(cfg)
+        hf = hf_model(cfg, sd, "sdpa")
+        dm = DistributedModel(hf, training=False, max_batch=2, max_seq=64)
+        assert dm.cfg.hidden == cfg.hidden and dm.cfg.qk_norm == cfg.qk_norm and dm.cfg.tied == cfg.tied
+        out_sd = dm.state_dict()
+        for k, v in sd.items():
+            assert torch.equal(out_sd[k].cpu(), v), k
+        ids = synthetic_tokens(cfg, 2, 20)
+        with torch.no_grad():
+            ref = hf(input_ids=ids).logits
+            ref32 = O.OracleModel(cfg, {k: v.float() for k, v in sd.items()}, "sdpa_math").logits(ids)
+        got = dm(input_ids=ids).logits.cpu()
+        e_ref, e_gpu = O.rel_l2(ref, ref32), O.rel_l2(got, ref32)
+        assert e_gpu <= 1.25 * e_ref, (e_gpu, e_ref)
+        assert len(list(dm.parameters())) == len(out_sd)
+
+
+def test_generate_edge_cases():
+    from tensorlink_b200.ml import DistributedModel
+    cfg = C.TINY_QWEN2_D128
+    dm = DistributedModel(cfg, training=False, max_batch=3, max_seq=48)
+    one = synthetic_tokens(cfg, 1, 1)
+    g = dm.generate(one, max_new_tokens=1)
+    assert g.shape == (1, 2) and int(g[0, 0]) == int(one[0, 0])
+    g3 = dm.generate(synthetic_tokens(cfg, 3, 7), max_new_tokens=5)          # odd batch (GEMV path with M = 3)
+    assert g3.shape == (3, 12)
+    full = dm.generate(synthetic_tokens(cfg, 1, 40), max_new_tokens=8)       # fills the cache exactly (40 + 8 = 48)
+    assert full.shape == (1, 48)
+    with pytest.raises(ValueError):
+        dm.generate(synthetic_tokens(cfg, 1, 41), max_new_tokens=8)          # would overflow the KV cache: loud
+    with pytest.raises(ValueError):
+        dm.generate(synthetic_tokens(cfg, 4, 4), max_new_tokens=2)           # more rows than the stage was sized for
+    with pytest.raises(NotImplementedError):
+        dm.generate(one, max_new_tokens=2, do_sample=True)
+    with pytest.raises(NotImplementedError):
+        DistributedModel(cfg, training=False, dtype=torch.float32)
+
+
+def test_forward_kwargs_and_train_eval_switch():
+    from tensorlink_b200.ml import DistributedModel
+    cfg = C.TINY_QWEN2
+    dm = DistributedModel(cfg, training=True, max_batch=2, max_seq=32, optimizer=torch.optim.AdamW)
+    ids = synthetic_tokens(cfg, 2, 16)
+    dm.eval()
+    a = dm(ids).logits                       # positional (module.py:355-359)
+    b = dm(input_ids=ids).logits             # keyword
+    assert torch.equal(a, b)
+    dm.train()
+    with pytest.raises(ValueError):
+        dm(ids)                              # training forward needs labels
+    out = dm(ids, labels=ids)
+    assert out.logits is None and out.loss.requires_grad
+    out.loss.backward()
+    opt = dm.create_optimizer(lr=1e-3, weight_decay=0.1)
+    opt.step()
+    opt.zero_grad()
+    assert float(dm.stage.params.grad.float().abs().sum()) == 0.0
