@@ -137,8 +137,8 @@ class ShardParams:
             out["model.embed_tokens.weight"] = src["embed"].clone()
         if self.has_head:
             out["model.norm.weight"] = src["norm"].clone()
-            if not (cfg.tied and self.has_embed):
-                out["lm_head.weight"] = src["head"].clone()
+            # tied heads appear under both names, like HF's own state_dict()
+            out["lm_head.weight"] = out["model.embed_tokens.weight"] if (cfg.tied and self.has_embed) else src["head"].clone()
         return out
 
     def init_seeded(self, seed: int = 1234):
