@@ -218,6 +218,8 @@ static int dispatch_g(int g, int wpi, const void* x, const void* W, void* y, int
 
 int gemv_stream_dispatch(const void* x, const void* W, void* y, int M, int N, int K, const void* bias,
                          const void* residual, const void* norm_w, float eps, int flags, cudaStream_t st);
+int gemv_mma_dispatch(const void* x, const void* W, void* y, int M, int N, int K, const void* bias, const void* residual,
+                      const void* norm_w, float eps, int flags, cudaStream_t st);
 
 static bool use_stream_kernel() {
     static int v = -1;
@@ -243,6 +245,13 @@ extern "C" int tl_gemv_bf16(const void* x, const void* W, void* y, int M, int N,
     TL_REQUIRE(!(flags & TL_EPI_BIAS) || bias, TL_ERR_INVALID, "tl_gemv_bf16: BIAS flag without bias pointer");
     TL_REQUIRE(!(flags & TL_EPI_RESIDUAL) || residual, TL_ERR_INVALID, "tl_gemv_bf16: RESIDUAL flag without pointer");
     cudaStream_t st = (cudaStream_t)stream;
+    if (M >= 2 && use_stream_kernel()) {      // 2..8 rows: tensor-core dot products on the same weight stream
+        const char* e = getenv("TL_GEMV_MMA");
+        if (!(e && e[0] == '0')) {
+            const int rc = gemv_mma_dispatch(x, W, y, M, N, K, bias, residual, norm_w, eps, flags, st);
+            if (rc != 1) return rc;
+        }
+    }
     const int nvec = K >> 3;
     int wpi = 1;
     while (wpi < 8 && (nvec + 32 * wpi - 1) / (32 * wpi) > 4) wpi <<= 1;

@@ -182,6 +182,29 @@ def test_gemv_bias_residual(nat, M, N, K):
     assert O.rel_l2(nat.gemv(dev(x), dev(w), residual=dev(r)).cpu(), r + F.linear(x, w)) <= TOL
 
 
+@pytest.mark.parametrize("M", [2, 3, 5, 8])
+@pytest.mark.parametrize("N,K,norm,mode", [(4608, 3584, True, "bias"), (3584, 18944, False, "res"), (896, 4864, False, "res"),
+                                           (9728, 896, True, "swiglu"), (37888, 3584, True, "swiglu"), (1152, 896, False, "plain")])
+def test_gemv_tensor_core_rows_2_to_8(nat, M, N, K, norm, mode):
+    """2..8 rows take the mma.sync weight-streaming kernel (resident x, or x chunks streamed when K is too large)."""
+    x, w = rnd(M, K, seed=41, std=2.0 if norm else 1.0), rnd(N, K, seed=42, std=0.05)
+    g = (1 + 0.1 * torch.randn(K)).bfloat16() if norm else None
+    h = O.rmsnorm(x, g, 1e-6) if norm else x
+    if mode == "bias":
+        b = rnd(N, seed=43, std=0.5)
+        got, ref = nat.gemv(dev(x), dev(w), bias=dev(b), norm_w=dev(g), eps=1e-6), F.linear(h, w, b)
+    elif mode == "res":
+        r = rnd(M, N, seed=44)
+        rd = dev(r.clone())
+        got, ref = nat.gemv(dev(x), dev(w), out=rd, residual=rd, norm_w=dev(g), eps=1e-6), r + F.linear(h, w)
+    elif mode == "swiglu":
+        y = F.linear(h, w)
+        got, ref = nat.gemv(dev(x), dev(w), norm_w=dev(g), eps=1e-6, flags=nat.EPI_SWIGLU), F.silu(y[:, 0::2]) * y[:, 1::2]
+    else:
+        got, ref = nat.gemv(dev(x), dev(w)), F.linear(h, w)
+    assert O.rel_l2(got.cpu(), ref) <= TOL
+
+
 @pytest.mark.parametrize("M,N,K", [(1, 1152, 896), (2, 4608, 3584), (4, 512, 256)])
 def test_gemv_norm_prologue(nat, M, N, K):
     x, w, b = rnd(M, K, seed=21, std=3.0), rnd(N, K, seed=22, std=0.05), rnd(N, seed=23, std=0.5)

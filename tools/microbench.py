@@ -49,7 +49,8 @@ def main():
     for (M, N, K, fl, nm) in [(1, 4608, 3584, 0, True), (1, 3584, 3584, 0, False), (1, 37888, 3584, nat.EPI_SWIGLU, True),
                               (1, 3584, 18944, 0, False), (1, 152064, 3584, 0, True), (4, 37888, 3584, nat.EPI_SWIGLU, True),
                               (1, 1152, 896, 0, True), (1, 9728, 896, nat.EPI_SWIGLU, True), (1, 896, 4864, 0, False),
-                              (1, 151936, 896, 0, True)]:
+                              (1, 151936, 896, 0, True), (2, 37888, 3584, nat.EPI_SWIGLU, True), (8, 37888, 3584, nat.EPI_SWIGLU, True),
+                              (4, 3584, 18944, 0, False), (8, 3584, 18944, 0, False), (8, 4608, 3584, 0, True)]:
         r = bench_gemv(M, N, K, fl, nm)
         print(json.dumps(r), flush=True)
         res.append(r)
