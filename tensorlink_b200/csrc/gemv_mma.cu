@@ -17,7 +17,7 @@ namespace tl {
 
 constexpr int GM_CONSUMER_WARPS = 8;
 constexpr int GM_THREADS = (GM_CONSUMER_WARPS + 1) * 32;
-constexpr int GM_KC = 512;                       // K chunk (elements) per stage
+constexpr int GM_KC = 1024;                      // K chunk (elements) per stage
 constexpr int GM_PITCH = GM_KC * 2 + 16;         // bytes per staged weight row
 constexpr int GM_STAGE_BYTES = 16 * GM_PITCH;    // 16,640 (weights only)
 constexpr int GM_STAGE_BYTES_X = 24 * GM_PITCH;  // 24,960 (weights + the 8-row x chunk, for K too large to keep x resident)
