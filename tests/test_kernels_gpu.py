@@ -185,8 +185,11 @@ def test_gemv_bias_residual(nat, M, N, K):
 @pytest.mark.parametrize("M", [2, 3, 5, 8])
 @pytest.mark.parametrize("N,K,norm,mode", [(4608, 3584, True, "bias"), (3584, 18944, False, "res"), (896, 4864, False, "res"),
                                            (9728, 896, True, "swiglu"), (37888, 3584, True, "swiglu"), (1152, 896, False, "plain")])
-def test_gemv_tensor_core_rows_2_to_8(nat, M, N, K, norm, mode):
-    """2..8 rows take the mma.sync weight-streaming kernel (resident x, or x chunks streamed when K is too large)."""
+@pytest.mark.parametrize("mma", ["0", "1"])
+def test_gemv_tensor_core_rows_2_to_8(nat, monkeypatch, mma, M, N, K, norm, mode):
+    """2..8 rows: the CUDA-core stream kernel (default) and the opt-in mma.sync kernel (TL_GEMV_MMA=1: resident x, or
+    x chunks streamed when K is too large) against the same oracle."""
+    monkeypatch.setenv("TL_GEMV_MMA", mma)
     x, w = rnd(M, K, seed=41, std=2.0 if norm else 1.0), rnd(N, K, seed=42, std=0.05)
     g = (1 + 0.1 * torch.randn(K)).bfloat16() if norm else None
     h = O.rmsnorm(x, g, 1e-6) if norm else x
