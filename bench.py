@@ -407,7 +407,8 @@ def main():
     roof["decode_step"] = {"algorithmic_bytes_per_pass_this_rank": step_bytes,
                            "achieved_GBps_whole_generate": step_bytes * passes / t_dev / 1e9,
                            "note": "whole timed region incl. prefill, attention, launch gaps and pipeline bubbles"}
-    launches = args.steps * (new - 1) * N * dm.stage.n_decode_launches(args.rows_per_gpu)
+    ring = getattr(dm, "_ring", None) is not None
+    launches = args.steps * (new - 1) * N * dm.stage.n_decode_launches(args.rows_per_gpu, ring=ring)
     line = dict(base, value=toks / t_dev, ms_per_step=t_dev / args.steps * 1e3,
                 e2e={"value": toks / t_e2e, "unit": "tokens/s", "h2d_bytes_per_step": rows * prompt * 8,
                      "d2h_bytes_per_step": rows * (prompt + new) * 8},
@@ -416,8 +417,12 @@ def main():
                           "decode_busy_frac_max_over_ranks": float(busy_max),
                           "exposed_wait_frac_worst_rank": 1.0 - float(busy_min),
                           "hop_bytes_per_token_step": args.rows_per_gpu * cfg.hidden * 2,
-                          "note": "CUDA events around every decode launch vs the whole decode phase, per rank; at N=1 the "
-                                  "remainder is host launch gaps only"})
+                          "hop": ("peer-mapped mailbox: the stage's last GEMV stores into the neighbour's HBM over NVLink, "
+                                  "release/acquire sequence number, no host in the loop (csrc/peer.cu)" if ring else
+                                  ("NCCL send/recv" if N > 1 else "none")),
+                          "note": ("whole decode phase minus the time the mailbox wait kernels spent spinning, per rank"
+                                   if ring else "CUDA events around every decode launch vs the whole decode phase, per "
+                                   "rank; at N=1 the remainder is host launch gaps only")})
     if not args.no_train:
         del dm
         torch.cuda.empty_cache()

@@ -156,6 +156,27 @@ size_t tl_decode_step_ws(int M);
 int tl_decode_step(const tl_decode_job* jobs_dev, const tl_decode_job* jobs_host, int n_jobs, int M, void* sync_ws,
                    void* stream);
 
+/* ---- peer-memory mailboxes: the inter-shard hop of a decode step (csrc/peer.cu) ---------------------------
+ * Replace the per-hop send of `DistributedModel.forward` (tensorlink/ml/module.py:438-462: tensor -> bytes ->
+ * shared memory -> node process -> socket) and the worker's pickup (tensorlink/ml/worker.py:297-305) on one
+ * NVSwitch node: the receiver's input buffer is mapped into the sender (CUDA IPC), the sender's last kernel stores
+ * its rows there over NVLink, and a sequence number published with release/acquire at system scope hands it over.
+ * All counters are device-resident and advance inside the kernels, so a captured CUDA graph replays unchanged. */
+/* cudaMalloc + zero `bytes` and export the allocation: handle64 = the 64-byte cudaIpcMemHandle_t */
+int tl_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);
+/* map another process's allocation (peer access enabled lazily); *ptr is valid on this process's device */
+int tl_peer_open(const unsigned char* handle64, void** ptr);
+int tl_peer_close(void* ptr);   /* unmap a tl_peer_open mapping */
+int tl_peer_free(void* ptr);    /* free a tl_peer_alloc allocation */
+/* ++*want_dev, then wait until *flag_local >= *want_dev (mod 2^32).  After timeout_ns (0 = 20 s) sets *err_dev = 1
+ * and returns instead of hanging.  wait_ns_dev (optional) accumulates the nanoseconds spent waiting. */
+int tl_peer_wait(const uint32_t* flag_local, uint32_t* want_dev, uint32_t* err_dev, uint64_t* wait_ns_dev,
+                 uint64_t timeout_ns, void* stream);
+/* ++*sent_dev, then publish it in the peer's flag after every earlier write of this stream (release, system scope) */
+int tl_peer_signal(uint32_t* flag_peer, uint32_t* sent_dev, void* stream);
+/* copy `bytes` (multiple of 16, both 16-byte aligned) into the peer buffer, then signal as above */
+int tl_peer_put(void* dst_peer, const void* src, size_t bytes, uint32_t* flag_peer, uint32_t* sent_dev, void* stream);
+
 /* ---- training-only pieces (K8/K9/K10): replace the autograd graph of `assoc_output.backward(loss)`
  * (tensorlink/ml/worker.py:271) and `optimizer.step()` (tensorlink/ml/worker.py:1317) ------------------------- */
 /* SwiGLU on interleaved gate/up pre-activations gu[M,2I] (col 2j = gate_j, 2j+1 = up_j): h[M,I], HF rounding */

@@ -194,6 +194,60 @@ class DistributedModel(torch.nn.Module):
         link.flush()
         return CausalLMOutput(logits=logits)
 
+    # ------------------------------------------------------------------------------------------ peer-memory decode
+    def _peer_ring(self, n_mb: int):
+        """The mailbox ring for decode hops (p2p/peer.py), or None: TL_P2P=nccl, or a stage that is not the CUDA one
+        (the gloo tests drive this class with a CPU stage).  Built collectively on first use."""
+        import os
+        from .stage import CudaStage
+        if os.environ.get("TL_P2P", "peer") == "nccl" or not isinstance(self.stage, CudaStage):
+            return None
+        if getattr(self, "_ring", None) is None:
+            from ..p2p.peer import PeerRing
+            st = self.stage
+            self._ring = PeerRing(self.link, len(st.slots), st.max_batch, self.cfg.hidden, st.max_seq, self.device)
+        return self._ring
+
+    def _decode_ring(self, ring, input_ids, B, S, b, n_mb, max_new, streamer, use_graph, profile, t0):
+        """Decode rounds with every hop on peer memory.  The host only enqueues: max_new-1 graph replays per
+        micro-batch (wait -> layers -> store into the neighbour -> signal), no synchronisation until the end; the
+        first stage logs each token column on the device (``ring.out_log``)."""
+        link, st, dev = self.link, self.stage, self.device
+        span = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        span[0].record()
+        step_done = []
+        for step in range(max_new):
+            for m in range(n_mb):
+                if step < max_new - 1:
+                    st.decode(m, b, use_graph, ring=ring)
+                elif link.first:                                   # last column: nothing left to compute
+                    ring.wait_ids(m)
+                    ring.log_token(m, b)
+            if streamer is not None and link.first:
+                ev = torch.cuda.Event()
+                ev.record()
+                step_done.append(ev)
+        span[1].record()
+        if streamer is not None and link.first:
+            for step, ev in enumerate(step_done):                  # step's graph logged column `step` before its event
+                ev.synchronize()
+                streamer.put(ring.out_log[:n_mb, :b, step].reshape(-1).cpu())
+        torch.cuda.synchronize(dev)
+        ring.check()
+        if profile:
+            self.timers["decode_span_s"] = span[0].elapsed_time(span[1]) * 1e-3
+            self.timers["decode_busy_s"] = self.timers["decode_span_s"] - float(ring.wait_ns.item()) * 1e-9
+        if link.first:
+            out_tokens = ring.out_log[:n_mb, :b, :max_new].reshape(B, max_new)
+            result = torch.cat([input_ids.to(dev), out_tokens], dim=1)
+        else:
+            result = torch.empty(B, S + max_new, dtype=torch.int64, device=dev)
+        link.broadcast(result, 0)
+        if streamer is not None and link.first:
+            streamer.end()
+        self.timers["generate_wall_s"] = time.perf_counter() - t0
+        return result
+
     # ------------------------------------------------------------------------------------------ generate
     @torch.no_grad()
     def generate(self, *args, **kwargs) -> Optional[torch.Tensor]:
@@ -225,6 +279,11 @@ class DistributedModel(torch.nn.Module):
 
         # ---- prefill every micro-batch through the pipeline; the last stage produces the first new token
         multi = self.world > 1
+        ring = self._peer_ring(n_mb) if multi else None
+        if ring is not None:
+            if max_new > ring.max_new:
+                raise ValueError(f"max_new_tokens {max_new} exceeds the token log of the peer ring ({ring.max_new})")
+            ring.reset()
         for m in range(n_mb):
             if link.first:
                 x = st.embed(ids_rows[m])
@@ -234,10 +293,15 @@ class DistributedModel(torch.nn.Module):
             x = st.prefill(x, 0, m)
             if not link.last:
                 link.send_next(x.clone())
+            elif ring is not None:                         # first token straight into the first stage's mailbox
+                st.head_argmax(x[:, -1, :].contiguous(), ring.first_ids_in[m][:b])
+                ring.signal_ids(m)
             else:
                 st.head_argmax(x[:, -1, :].contiguous(), st.ids_dec[m][:b])
                 if multi:
                     link.send_up(st.ids_dec[m][:b].clone(), 0)
+        if ring is not None:
+            return self._decode_ring(ring, input_ids, B, S, b, n_mb, max_new, streamer, use_graph, profile, t0)
         # ---- decode rounds: micro-batches rotate through the stages; hidden [b,H] hops down, ids hop back up.
         # Sends are asynchronous; a slot's buffer is waited on only right before the next step overwrites it.
         sent_x = [None] * n_mb

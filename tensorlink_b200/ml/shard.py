@@ -265,16 +265,16 @@ class CudaLayerGroup:
         nat.attn_decode_fwd(w.q, self.kc[j], self.vc[j], w.attn, self.kvlen_dev, self.dec_ws, B, cfg.n_heads,
                             cfg.n_kv_heads, cfg.head_dim, self.scale)
 
-    def _layer_decode(self, j: int, x: torch.Tensor, B: int, w: ShardBuffers):
+    def _layer_decode(self, j: int, x: torch.Tensor, B: int, w: ShardBuffers, out: Optional[torch.Tensor] = None):
         """Same layer for B <= 8 single-token rows: weight-streaming GEMVs with the norms fused as prologues."""
         cfg, v, li = self.cfg, self.p.v, self.layer_ids[j]
         nat.gemv(x, v[f"l{li}.wqkv"], out=w.qkv, bias=v.get(f"l{li}.bqkv"), norm_w=v[f"l{li}.ln1"], eps=cfg.rms_eps)
         self._decode_attention(j, li, B, w)
         nat.gemv(w.attn, v[f"l{li}.wo"], out=x, residual=x)
         nat.gemv(x, v[f"l{li}.wgu"], out=w.act, norm_w=v[f"l{li}.ln2"], eps=cfg.rms_eps, flags=nat.EPI_SWIGLU)
-        nat.gemv(w.act, v[f"l{li}.wd"], out=x, residual=x)
+        nat.gemv(w.act, v[f"l{li}.wd"], out=x if out is None else out, residual=x)
 
-    def _layer_decode_batched(self, j: int, x: torch.Tensor, B: int, w: ShardBuffers):
+    def _layer_decode_batched(self, j: int, x: torch.Tensor, B: int, w: ShardBuffers, out: Optional[torch.Tensor] = None):
         """B > 8 single-token rows: tcgen05 GEMMs in the weight-streaming regime (split along K where a Linear has too
         few output tiles to occupy every SM) + decode attention."""
         cfg, v, li = self.cfg, self.p.v, self.layer_ids[j]
@@ -285,7 +285,7 @@ class CudaLayerGroup:
         nat.gemm(w.attn, v[f"l{li}.wo"], out=x, residual=x, ws=ws)
         nat.rmsnorm_fwd(x, v[f"l{li}.ln2"], cfg.rms_eps, out=w.h)
         nat.gemm(w.h, v[f"l{li}.wgu"], out=w.act, flags=nat.EPI_SWIGLU, ws=ws)
-        nat.gemm(w.act, v[f"l{li}.wd"], out=x, residual=x, ws=ws)
+        nat.gemm(w.act, v[f"l{li}.wd"], out=x if out is None else out, residual=x, ws=ws)
 
     # ------------------------------------------------------------------------------------------ shard passes
     def prefill(self, hidden: torch.Tensor, past_len: int = 0) -> torch.Tensor:
@@ -303,18 +303,21 @@ class CudaLayerGroup:
         self.kvlen_dev.fill_(past_len + S)
         return w.x.view(B, S, H)
 
-    def decode_step_inplace(self, x: torch.Tensor):
+    def decode_step_inplace(self, x: torch.Tensor, out: Optional[torch.Tensor] = None):
         """x [B,H] updated in place through this shard's layers; one new token per row at position ``pos_dev``.
         Graph-capturable: the write position and the KV length live in device memory and are advanced by
-        kernels inside the same launch sequence (kv_len += 1 before the layers, pos += 1 after)."""
+        kernels inside the same launch sequence (kv_len += 1 before the layers, pos += 1 after).
+        ``out``: where the LAST layer's down projection stores the shard's output rows instead of ``x`` — the next
+        stage's peer-mapped input buffer (p2p/peer.py), so the hop rides on that kernel's own stores."""
         B = x.shape[0]
         w = self._dbufs(B)
         nat.advance_pos(self.kvlen_dev, None, 1)
         for j in range(self.num_layers):
+            o = out if j == self.num_layers - 1 else None
             if B <= 8:
-                self._layer_decode(j, x, B, w)
+                self._layer_decode(j, x, B, w, o)
             else:
-                self._layer_decode_batched(j, x, B, w)
+                self._layer_decode_batched(j, x, B, w, o)
         nat.advance_pos(self.pos_dev, None, 1)
 
     def decode_jobs(self, x: torch.Tensor, B: int) -> list:

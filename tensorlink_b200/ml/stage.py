@@ -106,7 +106,29 @@ class CudaStage:
             self.job_lists[key] = nat.DecodeJobList(jobs, self.device)
         return self.job_lists[key]
 
-    def _decode_body(self, slot: int, B: int):
+    def _decode_body_ring(self, slot: int, B: int, ring):
+        """The decode step of a multi-stage pipeline with the hops on peer memory (p2p/peer.py): wait for this slot's
+        input in the local mailbox, run the layers, let the last kernel store into the neighbour's mailbox, signal."""
+        if self.has_embed:
+            ring.wait_ids(slot)
+            ring.log_token(slot, B)
+            x = self.x_dec[slot][:B]
+            nat.embed_fwd(ring.ids_in[slot][:B], self.params.v["embed"], out=x)
+        else:
+            ring.wait_x(slot)
+            x = ring.x_in[slot][:B]
+        if self.has_head:
+            self.slots[slot].decode_step_inplace(x)
+            self.head_argmax(x, ring.first_ids_in[slot][:B])
+            ring.signal_ids(slot)
+        else:
+            self.slots[slot].decode_step_inplace(x, out=ring.next_x_in[slot][:B])
+            ring.signal_x(slot)
+
+    def _decode_body(self, slot: int, B: int, ring=None):
+        if ring is not None:
+            self._decode_body_ring(slot, B, ring)
+            return
         if self._use_step_kernel(B):
             nat.decode_step(self._step_jobs(slot, B), B, self.step_ws)
             return
@@ -117,13 +139,13 @@ class CudaStage:
         if self.has_head:
             self.head_argmax(x, self.ids_dec[slot][:B])
 
-    def decode(self, slot: int, B: int, use_graph: bool = True):
+    def decode(self, slot: int, B: int, use_graph: bool = True, ring=None):
         """One token for slot's rows: [embed ->] layers [-> norm + lm_head + argmax], as ONE graph launch.
-        Inputs/outputs are the fixed buffers ``ids_dec[slot]`` / ``x_dec[slot]``."""
+        Inputs/outputs are the fixed buffers ``ids_dec[slot]`` / ``x_dec[slot]``, or the mailboxes of ``ring``."""
         if not use_graph:
-            self._decode_body(slot, B)
+            self._decode_body(slot, B, ring)
             return
-        key = (slot, B)
+        key = (slot, B) if ring is None else (slot, B, id(ring))
         g = self.graphs.get(key)
         if g is None:
             # warm up outside capture (first-use attribute setting, tensor-map cache), restoring the state it touches
@@ -139,17 +161,19 @@ class CudaStage:
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._decode_body(slot, B)
+                self._decode_body(slot, B, ring)      # (the warm-up above never touches the mailboxes)
             # capture does not execute; state is still the saved one
             self.graphs[key] = g
         g.replay()
 
-    def n_decode_launches(self, B: int) -> int:
+    def n_decode_launches(self, B: int, ring: bool = False) -> int:
         """Kernel launches inside one decode step of this stage (for bench.py's gpu_launches claim)."""
         if self._use_step_kernel(B):
             return 1
         fused = self.slots[0].T_max <= self.slots[0].FUSED_DECODE_MAX_T
         n = len(self.slots[0].layer_ids) * ((7 if B <= 8 else 9) - (2 if fused else 0)) + 2
+        if ring:
+            n += 3 if self.has_embed else 2          # wait (+ token log) + signal
         if self.has_embed:
             n += 1
         if self.has_head:

@@ -46,6 +46,13 @@ _SIGS = {
     "tl_attn_decode_fused": (c_int, [c_void_p] * 9 + [c_float, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "tl_decode_step_ws": (c_size_t, [c_int]),
     "tl_decode_step": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "tl_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),
+    "tl_peer_open": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "tl_peer_close": (c_int, [c_void_p]),
+    "tl_peer_free": (c_int, [c_void_p]),
+    "tl_peer_wait": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_uint64, c_void_p]),
+    "tl_peer_signal": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "tl_peer_put": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "tl_lmhead_ws": (c_size_t, [c_int, c_int]),
     "tl_lmhead_argmax": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_size_t,
                                  c_int, c_int, c_int, c_void_p]),
@@ -297,6 +304,62 @@ def append_token(ids, out_tokens, step_dev):
     assert ids.dtype == torch.int64 and out_tokens.dtype == torch.int64 and out_tokens.is_contiguous()
     B, ld = out_tokens.shape
     _check(load().tl_append_token(_p(ids), _p(out_tokens), _p(step_dev), B, ld, _stream()), "tl_append_token")
+
+
+# ------------------------------------------------------------------------------------------ peer-memory mailboxes
+class _RawCuda:
+    """A raw device allocation seen through ``__cuda_array_interface__`` (bytes), so torch can view it."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3,
+                                         "strides": None}
+
+
+def tensor_from_ptr(ptr: int, nbytes: int) -> torch.Tensor:
+    """uint8 tensor over [ptr, ptr+nbytes) without taking ownership (the caller keeps the allocation alive).
+    No target device is named: torch tags the view with the device that owns the memory (for a peer mapping, the
+    neighbour's), and naming another one would silently turn the view into a copy.  Only ``data_ptr()`` of such a
+    view is ever used (as a kernel argument); torch never launches work on it."""
+    return torch.as_tensor(_RawCuda(ptr, nbytes))
+
+
+def peer_alloc(nbytes: int):
+    """(ptr, handle bytes[64]): zeroed device allocation exportable to other processes on this node."""
+    require_device()
+    ptr, h = c_void_p(), ctypes.create_string_buffer(64)
+    _check(load().tl_peer_alloc(nbytes, ctypes.byref(ptr), h), "tl_peer_alloc")
+    return ptr.value, bytes(h.raw)
+
+
+def peer_open(handle: bytes) -> int:
+    require_device()
+    ptr = c_void_p()
+    _check(load().tl_peer_open(ctypes.create_string_buffer(handle, 64), ctypes.byref(ptr)), "tl_peer_open")
+    return ptr.value
+
+
+def peer_close(ptr: int):
+    _check(load().tl_peer_close(ptr), "tl_peer_close")
+
+
+def peer_free(ptr: int):
+    _check(load().tl_peer_free(ptr), "tl_peer_free")
+
+
+def peer_wait(flag, want, err, wait_ns=None, timeout_ns: int = 0):
+    require_device()
+    _check(load().tl_peer_wait(_p(flag), _p(want), _p(err), _p(wait_ns), timeout_ns, _stream()), "tl_peer_wait")
+
+
+def peer_signal(flag_peer, sent):
+    require_device()
+    _check(load().tl_peer_signal(_p(flag_peer), _p(sent), _stream()), "tl_peer_signal")
+
+
+def peer_put(dst_peer, src, flag_peer, sent):
+    require_device()
+    nbytes = src.numel() * src.element_size()
+    _check(load().tl_peer_put(_p(dst_peer), _p(src), nbytes, _p(flag_peer), _p(sent), _stream()), "tl_peer_put")
 
 
 # ------------------------------------------------------------------------------------------ training wrappers

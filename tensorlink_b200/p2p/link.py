@@ -143,3 +143,10 @@ class StageLink:
         box = [obj]
         dist.broadcast_object_list(box, src=src, group=self.down)
         return box[0]
+
+    def all_gather_object(self, obj) -> list:
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        dist.all_gather_object(out, obj, group=self.down)
+        return out

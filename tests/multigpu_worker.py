@@ -32,6 +32,28 @@ def main(out_dir):
         res["logits_equal"] = bool(torch.equal(out.logits, ref_logits))
         res["gen_equal"] = bool(torch.equal(gen, ref_gen))
     res["gen_graph_vs_eager"] = bool(torch.equal(gen, gen_ng))
+    # the two generations above hopped over peer-mapped mailboxes (p2p/peer.py); NCCL send/recv must give the same ids
+    res["used_ring"] = getattr(dm, "_ring", None) is not None
+    os.environ["TL_P2P"] = "nccl"
+    gen_nccl = dm.generate(ids if rank == 0 else None, max_new_tokens=24)
+    os.environ.pop("TL_P2P")
+    res["gen_peer_vs_nccl"] = bool(torch.equal(gen, gen_nccl))
+
+    class Cols:
+        def __init__(self):
+            self.cols, self.ended = [], False
+
+        def put(self, t):
+            self.cols.append(t.clone())
+
+        def end(self):
+            self.ended = True
+
+    sink = Cols()
+    gen_s = dm.generate(ids if rank == 0 else None, max_new_tokens=6, streamer=sink)
+    if rank == 0:
+        res["stream_ok"] = bool(sink.ended and len(sink.cols) == 6 and
+                                torch.equal(torch.stack(sink.cols, 1).cuda(), gen_s[:, 20:]) and torch.equal(gen_s, gen[:, :26]))
     res["bytes_sent_infer"] = dm.link.bytes_sent
     # training: 2 micro-batches through the 2 stages
     tids = synthetic_tokens(cfg, 4, 32).cuda()

@@ -367,3 +367,41 @@ def test_argmax_ties_pick_lowest_index(nat):
     ws = torch.empty(3 * 64 * 8, dtype=torch.uint8, device="cuda")
     nat.argmax_bf16(dev(logits), ids, ws)
     assert ids.cpu().tolist() == [17, 4097, 0]
+
+
+# ------------------------------------------------------------------------------------------ peer-memory mailbox
+def test_peer_wait_signal_put(nat):
+    """A waiter on one stream is released by a put on another: payload first, then the sequence number (csrc/peer.cu);
+    counters advance on the device; a wait nobody answers gives up after its timeout and raises the error word."""
+    import time
+    ptr, handle = nat.peer_alloc(8192)
+    assert len(handle) == 64
+    raw = nat.tensor_from_ptr(ptr, 8192)
+    assert raw.data_ptr() == ptr and int(raw.sum()) == 0
+    flag, buf = raw[:4].view(torch.int32), raw[256:256 + 2048].view(torch.bfloat16)
+    want, sent, err = (torch.zeros(1, dtype=torch.int32, device="cuda") for _ in range(3))
+    wait_ns = torch.zeros(1, dtype=torch.int64, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for rnd_i in range(3):
+        src = rnd(1024, seed=70 + rnd_i).cuda()
+        out = torch.empty(1024, dtype=torch.bfloat16, device="cuda")
+        torch.cuda.synchronize()
+        with torch.cuda.stream(s1):
+            nat.peer_wait(flag, want, err, wait_ns)
+            out.copy_(buf)
+        time.sleep(0.02)
+        with torch.cuda.stream(s2):
+            nat.peer_put(buf, src, flag, sent)
+        torch.cuda.synchronize()
+        assert torch.equal(out, src)
+        assert int(want) == rnd_i + 1 and int(sent) == rnd_i + 1 and int(flag) == rnd_i + 1 and int(err) == 0
+    assert int(wait_ns) > 3 * 5_000_000          # the three waits really waited (>= 3 x 20 ms sleeps, generous margin)
+    nat.peer_signal(flag, sent)                  # signal first, wait second: returns at once
+    nat.peer_wait(flag, want, err, wait_ns)
+    torch.cuda.synchronize()
+    assert int(err) == 0 and int(flag) == 4
+    nat.peer_wait(flag, want, err, None, timeout_ns=3_000_000)   # nobody signals 5: times out after 3 ms
+    torch.cuda.synchronize()
+    assert int(err) == 1
+    del raw, flag, buf
+    nat.peer_free(ptr)
