@@ -168,8 +168,8 @@ int tl_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);
 int tl_peer_open(const unsigned char* handle64, void** ptr);
 int tl_peer_close(void* ptr);   /* unmap a tl_peer_open mapping */
 int tl_peer_free(void* ptr);    /* free a tl_peer_alloc allocation */
-/* ++*want_dev, then wait until *flag_local >= *want_dev (mod 2^32).  After timeout_ns (0 = 20 s) sets *err_dev = 1
- * and returns instead of hanging.  wait_ns_dev (optional) accumulates the nanoseconds spent waiting. */
+/* ++*want_dev, then wait until *flag_local >= *want_dev (mod 2^32).  After timeout_ns (0 = 10 s) sets *err_dev = 1
+ * and returns instead of hanging; once *err_dev is set every later wait returns at once.  wait_ns_dev (optional) accumulates the nanoseconds spent waiting. */
 int tl_peer_wait(const uint32_t* flag_local, uint32_t* want_dev, uint32_t* err_dev, uint64_t* wait_ns_dev,
                  uint64_t timeout_ns, void* stream);
 /* ++*sent_dev, then publish it in the peer's flag after every earlier write of this stream (release, system scope) */

@@ -33,6 +33,7 @@ __global__ void peer_wait_kernel(const uint32_t* __restrict__ flag, uint32_t* __
     if (threadIdx.x != 0) return;
     const uint32_t w = *want + 1u;
     *want = w;
+    if (*err) return;                 // an earlier wait already gave up: do not stall the rest of the queue
     const uint64_t t0 = global_ns();
     uint64_t t = t0;
     // sequence numbers compare modulo 2^32
@@ -116,7 +117,7 @@ int tl_peer_wait(const uint32_t* flag_local, uint32_t* want_dev, uint32_t* err_d
                  void* stream) {
     TL_REQUIRE(flag_local && want_dev && err_dev, TL_ERR_INVALID, "tl_peer_wait: null pointer");
     peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flag_local, want_dev, err_dev, (unsigned long long*)wait_ns_dev,
-                                                         timeout_ns ? timeout_ns : 20000000000ull);
+                                                         timeout_ns ? timeout_ns : 10000000000ull);
     return check_launch("tl_peer_wait");
 }
 
