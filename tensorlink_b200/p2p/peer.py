@@ -58,6 +58,13 @@ class PeerRing:
         self.max_new = max_new
         self.out_log = torch.zeros(n_slots, max_batch, max_new, dtype=torch.int64, device=dev)
         self.step_dev = torch.zeros(n_slots, dtype=torch.int32, device=dev)
+        # first use of the mailbox kernels now, sequentially: CUDA's lazy module loading synchronises the context, which
+        # must never happen for the first time while a waiter of this process is already spinning
+        scratch = torch.zeros(4, dtype=torch.int32, device=dev)
+        nat.peer_signal(scratch[0:1], scratch[1:2])
+        nat.peer_wait(scratch[0:1], scratch[2:3], self.err, self.wait_ns)
+        nat.peer_put(self.x_in[0][0], self.x_in[0][0], scratch[0:1], scratch[1:2])
+        torch.cuda.synchronize(dev)
         link.barrier()
 
     def _views(self, base: int):

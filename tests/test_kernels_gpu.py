@@ -381,6 +381,15 @@ def test_peer_wait_signal_put(nat):
     flag, buf = raw[:4].view(torch.int32), raw[256:256 + 2048].view(torch.bfloat16)
     want, sent, err = (torch.zeros(1, dtype=torch.int32, device="cuda") for _ in range(3))
     wait_ns = torch.zeros(1, dtype=torch.int64, device="cuda")
+    # first use of each kernel sequentially: lazy module loading synchronises the context, which must not happen while
+    # a waiter is already spinning (the pipeline loads them when it instantiates its graphs, before any traffic)
+    nat.peer_put(buf, rnd(1024, seed=69).cuda(), flag, sent)
+    nat.peer_wait(flag, want, err, wait_ns)
+    nat.peer_signal(flag, sent)
+    nat.peer_wait(flag, want, err, wait_ns)
+    torch.cuda.synchronize()
+    assert int(want) == 2 and int(sent) == 2 and int(flag) == 2 and int(err) == 0
+    wait_ns.zero_()
     s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
     for rnd_i in range(3):
         src = rnd(1024, seed=70 + rnd_i).cuda()
@@ -393,13 +402,10 @@ def test_peer_wait_signal_put(nat):
         with torch.cuda.stream(s2):
             nat.peer_put(buf, src, flag, sent)
         torch.cuda.synchronize()
+        assert int(err) == 0
         assert torch.equal(out, src)
-        assert int(want) == rnd_i + 1 and int(sent) == rnd_i + 1 and int(flag) == rnd_i + 1 and int(err) == 0
+        assert int(want) == rnd_i + 3 and int(sent) == rnd_i + 3 and int(flag) == rnd_i + 3
     assert int(wait_ns) > 3 * 5_000_000          # the three waits really waited (>= 3 x 20 ms sleeps, generous margin)
-    nat.peer_signal(flag, sent)                  # signal first, wait second: returns at once
-    nat.peer_wait(flag, want, err, wait_ns)
-    torch.cuda.synchronize()
-    assert int(err) == 0 and int(flag) == 4
     nat.peer_wait(flag, want, err, None, timeout_ns=3_000_000)   # nobody signals 5: times out after 3 ms
     torch.cuda.synchronize()
     assert int(err) == 1
