@@ -39,3 +39,19 @@ def test_two_gpu_pipeline_equals_single_stage(tmp_path):
     t0, t1, tr = torch.load(tmp_path / "tied0.pt"), torch.load(tmp_path / "tied1.pt"), torch.load(tmp_path / "tied_ref.pt")
     assert torch.equal(t0, t1)                                        # both copies of the tied weight see the same gradient
     assert (t0.float() - tr.float()).norm() / tr.float().norm() < 5e-3   # = single-stage sum up to bf16 add order
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_peer_ring_generation(tmp_path, world):
+    """Decode hops over peer-mapped mailboxes (first, middle and last stages) = NCCL hops = one stage, bit for bit."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
+           "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "ring_worker.py"), str(tmp_path)]
+    r = subprocess.run(cmd, env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True, timeout=600)
+    errs = "".join(open(p).read() for p in sorted(map(str, tmp_path.glob("err*.txt"))))
+    assert r.returncode == 0, errs or r.stderr[-4000:]
+    for rank in range(world):
+        res = torch.load(tmp_path / f"ring{rank}.pt")
+        assert res["used_ring"] and res["repeatable"] and res["peer_vs_nccl"], (rank, res)
+    assert torch.load(tmp_path / "ring0.pt")["vs_single"]
