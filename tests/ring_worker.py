@@ -19,7 +19,7 @@ def main(out_dir):
     rank, world = dist.get_rank(), dist.get_world_size()
     cfg = C.TINY_QWEN2_D128
     res = {}
-    dm = DistributedModel(cfg, training=False, n_pipelines=world, max_batch=2, max_seq=96)
+    dm = DistributedModel(cfg, training=False, n_pipelines=world, max_batch=2 * world, max_seq=96)
     ids = synthetic_tokens(cfg, 2 * world, 16).cuda()
     gen = dm.generate(ids if rank == 0 else None, max_new_tokens=40)
     res["used_ring"] = getattr(dm, "_ring", None) is not None
