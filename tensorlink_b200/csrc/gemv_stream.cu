@@ -255,7 +255,15 @@ static int launch_stream(const void* x, const void* W, void* y, int N, int K, co
         const char* e = getenv("TL_GEMV_CTAS_PER_SM");
         per_sm = (e && e[0] == '2') ? 2 : 1;
     }
-    const int SMEM_CAP = per_sm == 2 ? 110 * 1024 : 220 * 1024;
+    // TL_GEMV_RING_KB (default 220): shared memory per CTA.  <= 110 leaves room for the NEXT kernel's CTA on the same
+    // SM, so under programmatic dependent launch its producer fills its ring while this kernel is still streaming.
+    static int ring_kb = 0;
+    if (ring_kb == 0) {
+        const char* e = getenv("TL_GEMV_RING_KB");
+        ring_kb = e ? atoi(e) : 220;
+        if (ring_kb < 48 || ring_kb > 220) ring_kb = 220;
+    }
+    const int SMEM_CAP = per_sm == 2 ? 110 * 1024 : ring_kb * 1024;
     static bool attr_done = false;
     if (!attr_done) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
