@@ -211,7 +211,8 @@ int tl_colsum(const void* dy, float* db_accum, int M, int N, int ld, void* strea
 int tl_f32_to_bf16_accum(const float* src, void* dst, size_t n, int accumulate, void* stream);
 /* a[n] += b[n] over bf16 (n %% 8 == 0) */
 int tl_add_inplace(void* a, const void* b, size_t n, void* stream);
-/* fused Adam / AdamW (torch.optim update rule, fp32 math and moments) over a flat bf16 parameter arena */
+/* fused Adam / AdamW (torch.optim update rule, fp32 math and moments) over a flat bf16 parameter arena
+ * (all four arrays 16-byte aligned; n arbitrary) */
 int tl_adamw_step(void* param, const void* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
                   float beta1, float beta2, float eps, float weight_decay, int step, int decoupled,
                   void* stream);

@@ -418,21 +418,52 @@ __global__ void add_inplace_kernel(uint4* __restrict__ a, const uint4* __restric
 
 // ------------------------------------------------------------------------------------------------ AdamW
 // torch.optim.Adam/AdamW update rule in fp32 on bf16 parameters, fp32 moments
+__device__ __forceinline__ void adamw_one(float& pw, float gr, float& mi, float& vi, float lr, float b1, float b2, float eps,
+                                          float wd, float bc1, float bc2_sqrt, int decoupled) {
+    if (wd != 0.f) {
+        if (decoupled) pw *= (1.0f - lr * wd);
+        else gr += wd * pw;
+    }
+    mi = b1 * mi + (1.0f - b1) * gr;
+    vi = b2 * vi + (1.0f - b2) * gr * gr;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pw = pw - (lr / bc1) * (mi / denom);
+}
+
+// 8 elements per thread and iteration: 16-byte accesses to p / g, 2 x 16 bytes to each moment (22 bytes of HBM
+// traffic per parameter: this sweep is 1/6 of a Qwen2.5-7B step at batch 8 x 512, so it has to run at copy speed)
 __global__ void adamw_kernel(bf16* __restrict__ p, const bf16* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                              size_t n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
                              int decoupled) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        float pw = bf2f(p[i]), gr = bf2f(g[i]);
-        if (wd != 0.f) {
-            if (decoupled) pw *= (1.0f - lr * wd);
-            else gr += wd * pw;
+    const size_t n8 = n >> 3;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        uint4 pu = reinterpret_cast<const uint4*>(p)[i];
+        const uint4 gu = ldg_nc_v4(reinterpret_cast<const uint4*>(g) + i);
+        float4 m0 = reinterpret_cast<const float4*>(m)[2 * i], m1 = reinterpret_cast<const float4*>(m)[2 * i + 1];
+        float4 v0 = reinterpret_cast<const float4*>(v)[2 * i], v1 = reinterpret_cast<const float4*>(v)[2 * i + 1];
+        uint32_t* p32 = reinterpret_cast<uint32_t*>(&pu);
+        const uint32_t* g32 = reinterpret_cast<const uint32_t*>(&gu);
+        float* mm[2] = {reinterpret_cast<float*>(&m0), reinterpret_cast<float*>(&m1)};
+        float* vv[2] = {reinterpret_cast<float*>(&v0), reinterpret_cast<float*>(&v1)};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float pa = bf16_lo(p32[j]), pb = bf16_hi(p32[j]);
+            float* mj = mm[j >> 1] + 2 * (j & 1);
+            float* vj = vv[j >> 1] + 2 * (j & 1);
+            adamw_one(pa, bf16_lo(g32[j]), mj[0], vj[0], lr, b1, b2, eps, wd, bc1, bc2_sqrt, decoupled);
+            adamw_one(pb, bf16_hi(g32[j]), mj[1], vj[1], lr, b1, b2, eps, wd, bc1, bc2_sqrt, decoupled);
+            p32[j] = pack_bf16(pa, pb);
         }
-        const float mi = b1 * m[i] + (1.0f - b1) * gr;
-        const float vi = b2 * v[i] + (1.0f - b2) * gr * gr;
-        m[i] = mi;
-        v[i] = vi;
-        const float denom = sqrtf(vi) / bc2_sqrt + eps;
-        p[i] = f2bf(pw - (lr / bc1) * (mi / denom));
+        reinterpret_cast<uint4*>(p)[i] = pu;
+        reinterpret_cast<float4*>(m)[2 * i] = m0; reinterpret_cast<float4*>(m)[2 * i + 1] = m1;
+        reinterpret_cast<float4*>(v)[2 * i] = v0; reinterpret_cast<float4*>(v)[2 * i + 1] = v1;
+    }
+    // tail (n % 8 elements)
+    for (size_t i = (n8 << 3) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float pw = bf2f(p[i]), mi = m[i], vi = v[i];
+        adamw_one(pw, bf2f(g[i]), mi, vi, lr, b1, b2, eps, wd, bc1, bc2_sqrt, decoupled);
+        m[i] = mi; v[i] = vi; p[i] = f2bf(pw);
     }
 }
 
@@ -574,9 +605,11 @@ int tl_adamw_step(void* param, const void* grad, float* exp_avg, float* exp_avg_
     using namespace tl;
     TL_REQUIRE(step >= 1, TL_ERR_INVALID, "tl_adamw_step: step must start at 1");
     if (!n) return TL_OK;
+    TL_REQUIRE(((((uintptr_t)param) | ((uintptr_t)grad) | ((uintptr_t)exp_avg) | ((uintptr_t)exp_avg_sq)) & 15) == 0, TL_ERR_INVALID,
+               "tl_adamw_step: arenas must be 16-byte aligned");
     const float bc1 = 1.0f - powf(beta1, (float)step);
     const float bc2s = sqrtf(1.0f - powf(beta2, (float)step));
-    adamw_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>((bf16*)param, (const bf16*)grad, exp_avg, exp_avg_sq, n, lr,
+    adamw_kernel<<<ew_grid((n + 7) / 8, 256), 256, 0, (cudaStream_t)stream>>>((bf16*)param, (const bf16*)grad, exp_avg, exp_avg_sq, n, lr,
                                                                     beta1, beta2, eps, weight_decay, bc1, bc2s, decoupled);
     return check_launch("tl_adamw_step");
 }
