@@ -206,7 +206,7 @@ def measure_training(args, N, rank, world, tf_peak, peak_kind):
     from tensorlink_b200.ml.weights import synthetic_tokens
     cfg = get_config(args.train_model)
     B, S = args.train_batch * N, args.train_seq
-    n_mb = N if N == 1 else 2 * N           # more micro-batches than stages: pipeline bubble (N-1)/(n_mb+N-1)
+    n_mb = N if N == 1 else args.train_mb_per_stage * N    # more micro-batches than stages: bubble (N-1)/(n_mb+N-1)
     dm = DistributedModel(args.train_model, training=True, n_pipelines=n_mb, max_batch=B, max_seq=S, init="device",
                           optimizer=torch.optim.Adam, max_tokens=8, balanced_plan=N > 1)
     opt = dm.create_optimizer(lr=1e-4)
@@ -291,6 +291,7 @@ def main():
     ap.add_argument("--train-model", default="Qwen/Qwen2.5-7B")
     ap.add_argument("--train-batch", type=int, default=8)
     ap.add_argument("--train-seq", type=int, default=512)
+    ap.add_argument("--train-mb-per-stage", type=int, default=2, help="micro-batches per pipeline stage in the training step (N > 1)")
     args = ap.parse_args()
     name, prompt, new = WORKLOADS[args.workload]
     prompt, new = args.prompt or prompt, args.new or new
@@ -445,7 +446,7 @@ def main():
         if N == 1 and not args.no_cpu_baseline:
             ref = CpuReference(cfg, rows, prompt, budget_layers=1 if cfg.hidden > 2048 else 2)
             ref.run(new, 1)
-            v, sample = ref.run(new, 4)
+            v, sample = ref.run(new, 12)
             line["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": ref.threads, "kind": "port", "sample": sample}
         emit(line)
     if world > 1:
