@@ -76,6 +76,12 @@ int tl_gemm_bf16_ws(const void* A, const void* B, void* C, int M, int N, int K, 
  * y[M,N] = f(norm(x)[M,K] * W[N,K]^T).  norm_w != NULL fuses the preceding RMSNorm (K1) as a prologue. */
 int tl_gemv_bf16(const void* x, const void* W, void* y, int M, int N, int K, const void* bias,
                  const void* residual, const void* norm_w, float eps, int flags, void* stream);
+/* same, plus a hint: once its own weight loads are issued the kernel queues L2 prefetches of the first next_bytes of
+ * next_W (the weights the NEXT launch on this stream will read; 16-byte aligned, may be NULL), so HBM keeps streaming
+ * across the launch boundary and the next kernel starts from L2.  Purely a performance hint: results are identical. */
+int tl_gemv_bf16_pf(const void* x, const void* W, void* y, int M, int N, int K, const void* bias,
+                    const void* residual, const void* norm_w, float eps, int flags, const void* next_W,
+                    size_t next_bytes, void* stream);
 
 /* ---- K3  rotary tables (modeling_qwen2.py:102-113): cos/sin[pos, d/2] = bf16(cos/sin(pos * inv_freq)) */
 int tl_rope_table(const float* inv_freq, void* cos_tab, void* sin_tab, int max_pos, int half_dim, void* stream);

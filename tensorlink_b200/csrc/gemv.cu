@@ -217,7 +217,8 @@ static int dispatch_g(int g, int wpi, const void* x, const void* W, void* y, int
 }
 
 int gemv_stream_dispatch(const void* x, const void* W, void* y, int M, int N, int K, const void* bias,
-                         const void* residual, const void* norm_w, float eps, int flags, cudaStream_t st);
+                         const void* residual, const void* norm_w, float eps, int flags, const void* pf_ptr, size_t pf_bytes,
+                         cudaStream_t st);
 int gemv_mma_dispatch(const void* x, const void* W, void* y, int M, int N, int K, const void* bias, const void* residual,
                       const void* norm_w, float eps, int flags, cudaStream_t st);
 
@@ -232,8 +233,18 @@ static bool use_stream_kernel() {
 
 }  // namespace tl
 
+extern "C" int tl_gemv_bf16_pf(const void* x, const void* W, void* y, int M, int N, int K, const void* bias,
+                               const void* residual, const void* norm_w, float eps, int flags, const void* next_W,
+                               size_t next_bytes, void* stream);
+
 extern "C" int tl_gemv_bf16(const void* x, const void* W, void* y, int M, int N, int K, const void* bias,
                             const void* residual, const void* norm_w, float eps, int flags, void* stream) {
+    return tl_gemv_bf16_pf(x, W, y, M, N, K, bias, residual, norm_w, eps, flags, nullptr, 0, stream);
+}
+
+extern "C" int tl_gemv_bf16_pf(const void* x, const void* W, void* y, int M, int N, int K, const void* bias,
+                               const void* residual, const void* norm_w, float eps, int flags, const void* next_W,
+                               size_t next_bytes, void* stream) {
     using namespace tl;
     TL_REQUIRE(M >= 1 && M <= 8, TL_ERR_INVALID, "tl_gemv_bf16: M=%d outside 1..8 (use tl_gemm_bf16)", M);
     TL_REQUIRE(K % 8 == 0 && N % 2 == 0 && N > 0 && K > 0, TL_ERR_INVALID,
@@ -268,9 +279,10 @@ extern "C" int tl_gemv_bf16(const void* x, const void* W, void* y, int M, int N,
     // the M template is rounded up to 1/2/4/8 and the surplus rows are never written because the epilogue
     // indexes only m < M... (rows beyond M would read x out of bounds), so dispatch exactly for 1..4 and
     // split larger M into two calls.
-    auto run = [&](int m, const bf16* xx, bf16* yy, const bf16* rr) -> int {
+    auto run = [&](int m, const bf16* xx, bf16* yy, const bf16* rr, bool last) -> int {
         if (use_stream_kernel()) {
-            const int rc = gemv_stream_dispatch(xx, W, yy, m, N, K, bias, rr, norm_w, eps, flags, st);
+            const int rc = gemv_stream_dispatch(xx, W, yy, m, N, K, bias, rr, norm_w, eps, flags, last ? next_W : nullptr,
+                                                last && next_W ? next_bytes : 0, st);
             if (rc != 1) return rc;
         }
         switch (m) {
@@ -285,7 +297,7 @@ extern "C" int tl_gemv_bf16(const void* x, const void* W, void* y, int M, int N,
     while (done < M) {
         const int m = (M - done) > 4 ? 4 : (M - done);
         int rc = run(m, (const bf16*)x + (size_t)done * K, (bf16*)y + (size_t)done * n_out,
-                     residual ? (const bf16*)residual + (size_t)done * N : nullptr);
+                     residual ? (const bf16*)residual + (size_t)done * N : nullptr, done + m == M);
         if (rc != TL_OK) return rc;
         done += m;
     }

@@ -29,7 +29,8 @@ template <int M>
 __global__ void __launch_bounds__(GS_THREADS, 1)
 gemv_stream_kernel(const bf16* __restrict__ x, const bf16* __restrict__ W, bf16* __restrict__ y, int N, int K,
                    const bf16* __restrict__ bias, const bf16* __restrict__ residual, const bf16* __restrict__ norm_w,
-                   float eps, int flags, int P, int n_stages, int NW, int stage_bytes) {
+                   float eps, int flags, int P, int n_stages, int NW, int stage_bytes, const unsigned char* __restrict__ pf_ptr,
+                   unsigned long long pf_bytes) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* ring = smem;                                                    // [n_stages][stage_bytes]
     bf16* xs = reinterpret_cast<bf16*>(smem + (size_t)n_stages * stage_bytes);     // [M][K]
@@ -90,6 +91,18 @@ gemv_stream_kernel(const bf16* __restrict__ x, const bf16* __restrict__ W, bf16*
                         }
                         if (++stage == n_stages) { stage = 0; phase ^= 1; }
                     }
+                }
+            }
+            // every load of this CTA is issued (the last ring-full is still in flight): queue L2 prefetches of this
+            // CTA's slice of the NEXT kernel's weights behind them, so HBM keeps streaming through this kernel's tail,
+            // the launch boundary and the next kernel's prologue; the next kernel then fills its ring from L2.
+            if (pf_bytes) {
+                const unsigned long long per = ((pf_bytes / gridDim.x) + 4095ull) & ~4095ull;
+                unsigned long long off = (unsigned long long)blockIdx.x * per;
+                const unsigned long long end = off + per < pf_bytes ? off + per : pf_bytes;
+                for (; off < end; off += 16384ull) {
+                    const uint32_t sz = (uint32_t)(end - off < 16384ull ? end - off : 16384ull);
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf_ptr + off), "r"(sz) : "memory");
                 }
             }
         }
@@ -246,7 +259,7 @@ gemv_stream_kernel(const bf16* __restrict__ x, const bf16* __restrict__ W, bf16*
 
 template <int M>
 static int launch_stream(const void* x, const void* W, void* y, int N, int K, const void* bias, const void* residual,
-                         const void* norm_w, float eps, int flags, cudaStream_t st) {
+                         const void* norm_w, float eps, int flags, const void* pf_ptr, size_t pf_bytes, cudaStream_t st) {
     auto kern = gemv_stream_kernel<M>;
     // TL_GEMV_CTAS_PER_SM=2: two half-size rings per SM (16 consumer warps, finer work split, and the next kernel's
     // CTAs can become resident as soon as one of the two exits); 1 = one deep ring per SM
@@ -307,19 +320,22 @@ static int launch_stream(const void* x, const void* W, void* y, int N, int K, co
     cfg.attrs = attr;
     cfg.numAttrs = use_pdl ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kern, (const bf16*)x, (const bf16*)W, (bf16*)y, N, K, (const bf16*)bias, (const bf16*)residual,
-                       (const bf16*)norm_w, eps, flags, P, n_stages, NW, stage_bytes);
+                       (const bf16*)norm_w, eps, flags, P, n_stages, NW, stage_bytes, (const unsigned char*)pf_ptr,
+                       (unsigned long long)(pf_bytes & ~(size_t)15));
     return check_launch("tl_gemv_bf16/stream");
 }
 
 // returns TL_OK, an error, or 1 = "not applicable, use the fallback kernel"
 int gemv_stream_dispatch(const void* x, const void* W, void* y, int M, int N, int K, const void* bias,
-                         const void* residual, const void* norm_w, float eps, int flags, cudaStream_t st) {
+                         const void* residual, const void* norm_w, float eps, int flags, const void* pf_ptr, size_t pf_bytes,
+                         cudaStream_t st) {
     if (K % 8 != 0 || ((uintptr_t)W & 15)) return 1;
+    if ((uintptr_t)pf_ptr & 15) pf_bytes = 0;
     switch (M) {
-        case 1: return launch_stream<1>(x, W, y, N, K, bias, residual, norm_w, eps, flags, st);
-        case 2: return launch_stream<2>(x, W, y, N, K, bias, residual, norm_w, eps, flags, st);
-        case 3: return launch_stream<3>(x, W, y, N, K, bias, residual, norm_w, eps, flags, st);
-        case 4: return launch_stream<4>(x, W, y, N, K, bias, residual, norm_w, eps, flags, st);
+        case 1: return launch_stream<1>(x, W, y, N, K, bias, residual, norm_w, eps, flags, pf_ptr, pf_bytes, st);
+        case 2: return launch_stream<2>(x, W, y, N, K, bias, residual, norm_w, eps, flags, pf_ptr, pf_bytes, st);
+        case 3: return launch_stream<3>(x, W, y, N, K, bias, residual, norm_w, eps, flags, pf_ptr, pf_bytes, st);
+        case 4: return launch_stream<4>(x, W, y, N, K, bias, residual, norm_w, eps, flags, pf_ptr, pf_bytes, st);
         default: return 1;
     }
 }

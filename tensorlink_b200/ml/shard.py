@@ -195,6 +195,9 @@ class CudaLayerGroup:
                    for _ in self.layer_ids]
         self.vc = [torch.zeros_like(k) for k in self.kc]
         self.cos, self.sin = nat.rope_table(_rope_inv_freq(cfg).to(dev), max_seq)
+        # what the launch after this shard's last decode GEMV streams (a prefetch hint only, see _layer_decode)
+        self.weights_after_last_layer = (params.v.get("head") if "head" in params.v else
+                                         params.v.get(f"l{self.layer_ids[0]}.wqkv") if len(self.layer_ids) else None)
         self.pos_dev = torch.zeros(1, dtype=torch.int32, device=dev)      # next write position in the cache
         self.kvlen_dev = torch.zeros(1, dtype=torch.int32, device=dev)    # valid keys for the decode kernel
         self.n_max = max_tokens or max_batch * max_seq
@@ -268,11 +271,19 @@ class CudaLayerGroup:
     def _layer_decode(self, j: int, x: torch.Tensor, B: int, w: ShardBuffers, out: Optional[torch.Tensor] = None):
         """Same layer for B <= 8 single-token rows: weight-streaming GEMVs with the norms fused as prologues."""
         cfg, v, li = self.cfg, self.p.v, self.layer_ids[j]
-        nat.gemv(x, v[f"l{li}.wqkv"], out=w.qkv, bias=v.get(f"l{li}.bqkv"), norm_w=v[f"l{li}.ln1"], eps=cfg.rms_eps)
+        # every GEMV names the weights of the launch after it: it queues L2 prefetches behind its own loads, so HBM keeps
+        # streaming through the launch boundary (and through the attention kernel) instead of idling there
+        if j + 1 < self.num_layers:
+            after = v[f"l{self.layer_ids[j + 1]}.wqkv"]
+        else:
+            after = self.weights_after_last_layer            # lm_head on the last stage, else layer 0 for the next slot
+        nat.gemv(x, v[f"l{li}.wqkv"], out=w.qkv, bias=v.get(f"l{li}.bqkv"), norm_w=v[f"l{li}.ln1"], eps=cfg.rms_eps,
+                 next_w=v[f"l{li}.wo"])
         self._decode_attention(j, li, B, w)
-        nat.gemv(w.attn, v[f"l{li}.wo"], out=x, residual=x)
-        nat.gemv(x, v[f"l{li}.wgu"], out=w.act, norm_w=v[f"l{li}.ln2"], eps=cfg.rms_eps, flags=nat.EPI_SWIGLU)
-        nat.gemv(w.act, v[f"l{li}.wd"], out=x if out is None else out, residual=x)
+        nat.gemv(w.attn, v[f"l{li}.wo"], out=x, residual=x, next_w=v[f"l{li}.wgu"])
+        nat.gemv(x, v[f"l{li}.wgu"], out=w.act, norm_w=v[f"l{li}.ln2"], eps=cfg.rms_eps, flags=nat.EPI_SWIGLU,
+                 next_w=v[f"l{li}.wd"])
+        nat.gemv(w.act, v[f"l{li}.wd"], out=x if out is None else out, residual=x, next_w=after)
 
     def _layer_decode_batched(self, j: int, x: torch.Tensor, B: int, w: ShardBuffers, out: Optional[torch.Tensor] = None):
         """B > 8 single-token rows: tcgen05 GEMMs in the weight-streaming regime (split along K where a Linear has too

@@ -35,6 +35,8 @@ _SIGS = {
                                 c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "tl_gemv_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                              c_float, c_int, c_void_p]),
+    "tl_gemv_bf16_pf": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                c_float, c_int, c_void_p, c_size_t, c_void_p]),
     "tl_rope_table": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "tl_rope_kv_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_float, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
@@ -214,8 +216,19 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
     return out
 
 
+_PREFETCH_BYTES = None
+
+
+def prefetch_bytes() -> int:
+    """How much of the next launch's weights a GEMV asks L2 to fetch (TL_PREFETCH_MB, default 32; 0 disables)."""
+    global _PREFETCH_BYTES
+    if _PREFETCH_BYTES is None:
+        _PREFETCH_BYTES = int(float(os.environ.get("TL_PREFETCH_MB", "32")) * (1 << 20))
+    return _PREFETCH_BYTES
+
+
 def gemv(x: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, *, bias=None, residual=None,
-         norm_w=None, eps: float = 1e-6, flags: int = 0) -> torch.Tensor:
+         norm_w=None, eps: float = 1e-6, flags: int = 0, next_w: Optional[torch.Tensor] = None) -> torch.Tensor:
     require_device()
     _bf16(x, w, bias, residual, norm_w, out)
     M, K = x.shape
@@ -226,6 +239,11 @@ def gemv(x: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, *
         flags |= EPI_BIAS
     if residual is not None:
         flags |= EPI_RESIDUAL
+    if next_w is not None and prefetch_bytes() > 0:
+        nb = min(next_w.numel() * next_w.element_size(), prefetch_bytes())
+        _check(load().tl_gemv_bf16_pf(_p(x), _p(w), _p(out), M, N, K, _p(bias), _p(residual), _p(norm_w), eps, flags,
+                                      _p(next_w), nb, _stream()), "tl_gemv_bf16_pf")
+        return out
     _check(load().tl_gemv_bf16(_p(x), _p(w), _p(out), M, N, K, _p(bias), _p(residual), _p(norm_w), eps, flags,
                                _stream()), "tl_gemv_bf16")
     return out
