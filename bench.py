@@ -101,6 +101,21 @@ def usable_cores():
     return n
 
 
+def reference_hop_times(cfg, rows, prompt):
+    """The reference's wire path for one shard boundary (oracle/wire_oracle.py: encode -> shared-memory hand-overs ->
+    decode, utils.py:569-660 + shared_memory.py), timed on this host for the decode and the prefill payload of this
+    workload with ONLY ``hidden_states`` in the payload — a lower bound: the reference also re-ships masks, rotary
+    tables and the KV cache, crosses a TCP socket and sleeps 0.1 s per call."""
+    import torch
+    from oracle import wire_oracle as W
+    out = {"what": "tensor_to_bytes -> 3 x (store/get shared memory) -> bytes_to_tensor, hidden_states only, host CPU, "
+                   "median of repeats; no socket, no 0.1 s sleeps"}
+    for tag, S, reps in (("decode", 1, 50), ("prefill", prompt, 5)):
+        t = torch.zeros(rows, S, cfg.hidden, dtype=torch.bfloat16)
+        out[tag] = {"payload_bytes": t.numel() * 2, "seconds": W.time_reference_hop({"hidden_states": t}, repeats=reps)}
+    return out
+
+
 class CpuReference:
     """The reference's CPU shard math (oracle port of the HF decoder layers the reference executes) on a bounded
     sample: ``budget_layers`` of the model's layers at full width + the full-vocabulary lm_head, ``prompt``-token
@@ -330,7 +345,8 @@ def main():
                 vals.append(v)
         val = sum(vals) / len(vals)
         line = dict(base, impl="reference", value=val, ms_per_step=rows * new / val * 1e3,
-                    cpu_baseline={"value": val, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
+                    cpu_baseline={"value": val, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample,
+                                  "reference_hop": reference_hop_times(cfg, rows, prompt)},
                     e2e={"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                     gpu_launches=0)
         emit(line)
@@ -447,7 +463,8 @@ def main():
             ref = CpuReference(cfg, rows, prompt, budget_layers=1 if cfg.hidden > 2048 else 2)
             ref.run(new, 1)
             v, sample = ref.run(new, 12)
-            line["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": ref.threads, "kind": "port", "sample": sample}
+            line["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": ref.threads, "kind": "port", "sample": sample,
+                                    "reference_hop": reference_hop_times(cfg, rows, prompt)}
         emit(line)
     if world > 1:
         dist.barrier()

@@ -1,0 +1,43 @@
+"""Generate golden wire frames with the reference's OWN codec (tensorlink/ml/utils.py:569-660).  TEST INFRA.
+
+Run in the build container (needs /root/reference):  python -m oracle.gen_golden_wire
+Writes tests/golden/ref_wire_frames.pt: seeded payloads and the exact bytes ``tensor_to_bytes`` produced for them.
+"""
+import os
+
+import torch
+
+from oracle.ref_shim import import_reference
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "ref_wire_frames.pt")
+
+
+def payloads():
+    g = torch.Generator().manual_seed(77)
+    hs = torch.randn(2, 5, 64, generator=g).bfloat16()
+    cos, sin = torch.randn(2, 5, 16, generator=g).bfloat16(), torch.randn(2, 5, 16, generator=g).bfloat16()
+    return {
+        "decode_row": {"hidden_states": torch.randn(1, 1, 896, generator=g).bfloat16()},
+        "live_ins": {"hidden_states": hs, "position_ids": torch.arange(5)[None].expand(2, -1).contiguous(),
+                     "position_embeddings": (cos, sin), "use_cache": False, "past_key_values": None,
+                     "causal_mask": torch.zeros(2, 1, 5, 5).bfloat16(), "kwargs": {}},
+        "nested": [1, 2.5, "x", (torch.arange(6, dtype=torch.int64).view(2, 3), [torch.ones(3, dtype=torch.float32)])],
+        "no_tensors": {"a": 1, "b": [True, None]},
+        "dropped_object": {"keep": torch.zeros(2, dtype=torch.float16), "drop": object()},
+    }
+
+
+def main():
+    _, utils = import_reference()
+    items = payloads()
+    frames = {k: utils.tensor_to_bytes(v) for k, v in items.items()}
+    for k, f in frames.items():                       # the reference decodes its own frames back
+        back = utils.bytes_to_tensor(f)
+        assert type(back) is type(items[k]) or items[k] is None
+    items["dropped_object"]["drop"] = None            # what survives the reference codec (utils.py:607)
+    torch.save({"payloads": items, "frames": frames}, OUT)
+    print("wrote", OUT, {k: len(v) for k, v in frames.items()})
+
+
+if __name__ == "__main__":
+    main()
