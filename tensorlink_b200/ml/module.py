@@ -13,6 +13,8 @@ the last stage (pass ``gather_logits=True`` to copy them to rank 0).
 """
 from __future__ import annotations
 
+import os
+
 import time
 from dataclasses import dataclass
 from typing import Any, Callable, Dict, List, Optional, Union
@@ -69,6 +71,11 @@ class DistributedModel(torch.nn.Module):
             state_dict = model.state_dict()
         elif isinstance(model, ShardModelConfig):
             self.cfg = model
+        elif isinstance(model, str) and os.path.isdir(model) and os.path.exists(os.path.join(model, "config.json")):
+            # a local checkpoint in the HF layout: each stage reads only its own tensors (worker.py:542-638)
+            from .checkpoint import LazyCheckpoint, config_from_dir
+            self.cfg = config_from_dir(model)
+            state_dict = LazyCheckpoint(model)
         else:
             self.cfg = get_config(model)
         self.model_name = self.cfg.name
@@ -147,6 +154,11 @@ class DistributedModel(torch.nn.Module):
 
     def state_dict(self, *a, **k):
         return self.stage.params.hf_state_dict()
+
+    def save_pretrained(self, path: str):
+        """Write this job's weights as an HF-layout checkpoint (one safetensors file per stage + index + config)."""
+        from .checkpoint import save_checkpoint
+        save_checkpoint(self, path)
 
     def create_optimizer(self, **optimizer_kwargs):
         from .optim import create_distributed_optimizer
