@@ -54,4 +54,5 @@ def test_peer_ring_generation(tmp_path, world):
     for rank in range(world):
         res = torch.load(tmp_path / f"ring{rank}.pt")
         assert res["used_ring"] and res["repeatable"] and res["peer_vs_nccl"], (rank, res)
-    assert torch.load(tmp_path / "ring0.pt")["vs_single"]
+    r0 = torch.load(tmp_path / "ring0.pt")
+    assert r0["vs_single"] and r0["ckpt_roundtrip"] and len(r0["ckpt_files"]) == world
