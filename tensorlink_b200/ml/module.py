@@ -54,6 +54,26 @@ def _config_from_hf(model) -> ShardModelConfig:
                             rms_eps=float(c.rms_norm_eps), max_pos=int(c.max_position_embeddings))
 
 
+def apply_eos(result: torch.Tensor, prompt_len: int, eos_token_id=None, pad_token_id=None) -> torch.Tensor:
+    """HF ``generate`` stopping semantics applied to a finished greedy generation [B, S+new]: everything after a row's
+    first EOS becomes ``pad_token_id`` (default: the EOS id) and the result ends where the last row finished.
+    (The decode loop itself always runs ``max_new_tokens`` steps: the host never sees a token while they run.)"""
+    if eos_token_id is None:
+        return result
+    eos_ids = [int(e) for e in eos_token_id] if isinstance(eos_token_id, (list, tuple)) else [int(eos_token_id)]
+    pad = eos_ids[0] if pad_token_id is None else int(pad_token_id)
+    new = result[:, prompt_len:]
+    if new.shape[1] == 0:
+        return result
+    is_eos = torch.zeros_like(new, dtype=torch.bool)
+    for e in eos_ids:
+        is_eos |= new == e
+    seen_before = (is_eos.cumsum(1) - is_eos.long()) > 0
+    new = torch.where(seen_before, torch.full_like(new, pad), new)
+    first = torch.where(is_eos.any(1), is_eos.long().argmax(1) + 1, torch.full_like(new[:, 0], new.shape[1]))
+    return torch.cat([result[:, :prompt_len], new[:, :int(first.max())]], dim=1)
+
+
 class DistributedModel(torch.nn.Module):
     def __init__(self, model: Union[torch.nn.Module, str, ShardModelConfig], n_pipelines: int = 1,
                  optimizer=None, scheduler_type=None, device: Optional[str] = None,
@@ -258,7 +278,7 @@ class DistributedModel(torch.nn.Module):
         if streamer is not None and link.first:
             streamer.end()
         self.timers["generate_wall_s"] = time.perf_counter() - t0
-        return result
+        return apply_eos(result, S, *self._eos)
 
     # ------------------------------------------------------------------------------------------ generate
     @torch.no_grad()
@@ -274,7 +294,7 @@ class DistributedModel(torch.nn.Module):
         profile = kwargs.pop("profile", False)       # CUDA events around every decode launch -> self.timers["decode_busy_s"]
         if kwargs.pop("do_sample", False):
             raise NotImplementedError("sampling is not implemented; generate() is greedy (do_sample=False)")
-        kwargs.pop("eos_token_id", None); kwargs.pop("pad_token_id", None)
+        self._eos = (kwargs.pop("eos_token_id", None), kwargs.pop("pad_token_id", None))
         link, st, cfg = self.link, self.stage, self.cfg
         shape = link.broadcast_object(tuple(input_ids.shape) if link.first else None)
         B, S = shape
@@ -363,4 +383,4 @@ class DistributedModel(torch.nn.Module):
         if streamer is not None and link.first:
             streamer.end()
         self.timers["generate_wall_s"] = time.perf_counter() - t0
-        return result
+        return apply_eos(result, S, *self._eos)

@@ -84,3 +84,23 @@ def test_node_shim_contract():
         assert hasattr(u, attr)
     with pytest.raises(NotImplementedError):
         u.send_request("request_job", None)
+
+
+def test_apply_eos_matches_hf_generate_stopping():
+    """Host logic of generate(eos_token_id=..., pad_token_id=...): applied to a full greedy generation it must give
+    what HF's own stopping criteria give (rows padded after their first EOS, output ends when every row is done)."""
+    import torch
+    from tensorlink_b200.ml import configs as C
+    from tensorlink_b200.ml.module import apply_eos
+    from tensorlink_b200.ml.weights import init_state_dict, synthetic_tokens
+    from tests.hf_util import hf_model
+    cfg = C.TINY_QWEN2
+    hf = hf_model(cfg, init_state_dict(cfg, dtype=torch.float32), "eager", torch.float32)
+    ids = synthetic_tokens(cfg, 3, 6)
+    with torch.no_grad():
+        full = hf.generate(ids, max_new_tokens=12, do_sample=False, eos_token_id=None, pad_token_id=0)
+        for eos in (int(full[0, 8]), [int(full[1, 7]), int(full[2, 15])], int(full[0, 17]), cfg.vocab - 1):
+            want = hf.generate(ids, max_new_tokens=12, do_sample=False, eos_token_id=eos, pad_token_id=0)
+            got = apply_eos(full, 6, eos, 0)
+            assert got.shape == want.shape and torch.equal(got, want), eos
+    assert torch.equal(apply_eos(full, 6), full)
