@@ -174,10 +174,12 @@ def measure_gemv_launches(dm, rows):
     466 MB of weights, so nothing is L2-resident between launches).  Returns per-shape averages."""
     import torch
     from tensorlink_b200 import native as nat
+    from tensorlink_b200.ml.shard import gemv_max_rows
     st, cfg = dm.stage, dm.cfg
     grp = st.slots[0]
     v = st.params.v
     w = grp._bufs(rows)
+    use_gemv = rows <= gemv_max_rows()
     x = torch.randn(rows, cfg.hidden, device=dm.device).bfloat16()
     shapes = {"qkv": (cfg.qkv_dim, cfg.hidden), "o": (cfg.hidden, cfg.q_dim), "gate_up": (2 * cfg.intermediate, cfg.hidden),
               "down": (cfg.hidden, cfg.intermediate)}
@@ -185,7 +187,7 @@ def measure_gemv_launches(dm, rows):
     for rep in range(3):
         evs = []
         for li in grp.layer_ids:
-            if rows <= 4:
+            if use_gemv:
                 calls = (("qkv", lambda: nat.gemv(x, v[f"l{li}.wqkv"], out=w.qkv, bias=v.get(f"l{li}.bqkv"), norm_w=v[f"l{li}.ln1"], eps=cfg.rms_eps)),
                          ("o", lambda: nat.gemv(w.attn, v[f"l{li}.wo"], out=x, residual=x)),
                          ("gate_up", lambda: nat.gemv(x, v[f"l{li}.wgu"], out=w.act, norm_w=v[f"l{li}.ln2"], eps=cfg.rms_eps, flags=nat.EPI_SWIGLU)),
@@ -419,12 +421,14 @@ def main():
     # ---- dominant kernel, live: the weight-streaming GEMV
     hbm_peak, tf_peak, peak_kind = measured_peaks()
     gv = measure_gemv_launches(dm, args.rows_per_gpu)
+    from tensorlink_b200.ml.shard import gemv_max_rows
+    gemv_path = args.rows_per_gpu <= gemv_max_rows()
     tot_b = sum(v["bytes"] for v in gv.values()); tot_s = sum(v["s"] for v in gv.values())
     traffic = None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get(f"gemv_gate_up:{name}")
-    roof = {"bound": "hbm", "kernel": ("tl::gemv_stream_kernel (gate/up Linear, RMSNorm prologue + SwiGLU epilogue)" if args.rows_per_gpu <= 4
+    roof = {"bound": "hbm", "kernel": ("tl::gemv_stream_kernel (gate/up Linear, RMSNorm prologue + SwiGLU epilogue)" if gemv_path
                                        else "tl::gemm_bf16_kernel (gate/up Linear at M = rows, weight-streaming regime)"),
             "achieved": gv["gate_up"]["GBps"], "peak": hbm_peak, "peak_kind": f"{peak_kind} copy bandwidth (burst)",
             "unit": "GB/s", "frac": gv["gate_up"]["GBps"] / hbm_peak, "traffic": traffic,

@@ -28,6 +28,20 @@ from .weights import init_state_dict
 ALIGN = 128  # elements (256 B)
 
 
+_GEMV_MAX_ROWS = None
+
+
+def gemv_max_rows() -> int:
+    """Rows per decode step up to which the weight-streaming GEMV path is used; more rows go through the tcgen05 GEMM
+    path (one weight pass for all rows; the GEMV kernel needs a second pass above 4 rows and spends CUDA-core FMAs per
+    row).  TL_GEMV_MAX_ROWS overrides (1..8)."""
+    global _GEMV_MAX_ROWS
+    if _GEMV_MAX_ROWS is None:
+        import os
+        _GEMV_MAX_ROWS = max(1, min(8, int(os.environ.get("TL_GEMV_MAX_ROWS", "8"))))
+    return _GEMV_MAX_ROWS
+
+
 def _rope_inv_freq(cfg: ShardModelConfig) -> torch.Tensor:
     """site-packages/transformers/models/qwen2/modeling_qwen2.py:84-99, computed on the host in fp32 like HF."""
     d = cfg.head_dim
@@ -325,7 +339,7 @@ class CudaLayerGroup:
         nat.advance_pos(self.kvlen_dev, None, 1)
         for j in range(self.num_layers):
             o = out if j == self.num_layers - 1 else None
-            if B <= 8:
+            if B <= gemv_max_rows():
                 self._layer_decode(j, x, B, w, o)
             else:
                 self._layer_decode_batched(j, x, B, w, o)

@@ -13,7 +13,7 @@ import torch
 
 from .. import native as nat
 from .configs import ShardModelConfig
-from .shard import CudaLayerGroup, ShardParams
+from .shard import CudaLayerGroup, ShardParams, gemv_max_rows
 
 
 class CudaStage:
@@ -61,7 +61,7 @@ class CudaStage:
         """final norm + lm_head over [N,H] -> bf16 logits [N,V]."""
         cfg, v = self.cfg, self.params.v
         n = hidden.shape[0]
-        if n <= 8:
+        if n <= gemv_max_rows():
             return nat.gemv(hidden.contiguous(), v["head"], norm_w=v["norm"], eps=cfg.rms_eps)
         hn = nat.rmsnorm_fwd(hidden.contiguous(), v["norm"], cfg.rms_eps)
         return nat.gemm(hn, v["head"])
@@ -70,7 +70,7 @@ class CudaStage:
         """greedy next token for [B,H] rows -> ids_out [B] int64 (bit-exact target: torch.argmax of bf16 logits)."""
         cfg, v = self.cfg, self.params.v
         B = hidden.shape[0]
-        if B <= 8:
+        if B <= gemv_max_rows():
             nat.lmhead_argmax(hidden, v["head"], v["norm"], cfg.rms_eps, ids_out, self.logits_dec[:B], self.head_ws)
         else:
             nat.rmsnorm_fwd(hidden, v["norm"], cfg.rms_eps, out=self.hn[:B])
@@ -171,11 +171,11 @@ class CudaStage:
         if self._use_step_kernel(B):
             return 1
         fused = self.slots[0].T_max <= self.slots[0].FUSED_DECODE_MAX_T
-        n = len(self.slots[0].layer_ids) * ((7 if B <= 8 else 9) - (2 if fused else 0)) + 2
+        n = len(self.slots[0].layer_ids) * ((7 if B <= gemv_max_rows() else 9) - (2 if fused else 0)) + 2
         if ring:
             n += 3 if self.has_embed else 2          # wait (+ token log) + signal
         if self.has_embed:
             n += 1
         if self.has_head:
-            n += 3 if B <= 8 else 4
+            n += 3 if B <= gemv_max_rows() else 4
         return n
