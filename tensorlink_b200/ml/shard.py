@@ -217,9 +217,10 @@ class CudaLayerGroup:
         self.n_max = max_tokens or max_batch * max_seq
         self._alloc_bufs(min(self.n_max, 8))
         self.dbufs = self._make_bufs(max_batch)       # decode-time buffers: fixed addresses (captured graphs, job lists)
-        # split-K workspace for batched decode (8 < B <= 128): the qkv / o / down Linears have too few output tiles
+        # split-K workspace for batched decode (rows above the GEMV threshold, <= 128): the qkv / o / down Linears have
+        # too few output tiles to occupy every SM
         self.gemm_ws = (torch.empty(nat.gemm_splitk_ws(min(max_batch, 128), max(cfg.qkv_dim, cfg.hidden)), dtype=torch.uint8,
-                                    device=dev) if max_batch > 8 else None)
+                                    device=dev) if max_batch > 1 else None)
         self.dec_ws = torch.empty(max(nat.attn_decode_ws(max_batch, cfg.n_heads, cfg.head_dim, max_seq), 16),
                                   dtype=torch.uint8, device=dev)
         self.scale = cfg.head_dim ** -0.5
