@@ -71,6 +71,13 @@ int tl_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int
 size_t tl_gemm_splitk_ws(int M, int N);
 int tl_gemm_bf16_ws(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
                     const void* bias, const void* residual, int flags, void* workspace, size_t ws_bytes, void* stream);
+/* ... and the RMSNorm that follows this Linear in the decoder layer (modeling_qwen2.py:296 / :280 of the next layer):
+ * with norm_w != NULL also writes H_out[M,N] = norm_w * bf16(C * rstd(C)), C being the bf16 result above (ldc == N,
+ * bias / residual epilogue only).  Fused into the split-K reduce pass when that path runs, otherwise one extra
+ * tl_rmsnorm_fwd launch: identical bits either way. */
+int tl_gemm_bf16_ws_norm(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
+                         const void* bias, const void* residual, int flags, void* workspace, size_t ws_bytes,
+                         const void* norm_w, float eps, void* H_out, void* stream);
 
 /* ---- decode-shaped Linear (M <= 8 tokens), HBM-bound weight streaming:
  * y[M,N] = f(norm(x)[M,K] * W[N,K]^T).  norm_w != NULL fuses the preceding RMSNorm (K1) as a prologue. */

@@ -340,6 +340,83 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, void* __restr
     *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
 }
 
+// split-K reduce + epilogue (bias / residual, bf16 out) + the RMSNorm that follows the Linear, one CTA per row:
+// C[m,:] = bf16(bf16(sum_s ws[s][m][:] + bias) + residual[m,:]);  Hn[m,:] = norm_w * bf16(C[m,:] * rstd(C[m,:])).
+// Thread mapping and reduction order are those of rmsnorm_fwd_kernel, so Hn is bit-identical to running it on C.
+constexpr int RN_THREADS = 128;
+constexpr int RN_MAXV = 8;
+__global__ void __launch_bounds__(RN_THREADS)
+splitk_reduce_norm_kernel(const float* __restrict__ ws, bf16* __restrict__ C, int M, int N, int ldc, int splits,
+                          const bf16* __restrict__ bias, const bf16* __restrict__ residual, int ldr, int flags,
+                          const bf16* __restrict__ norm_w, float eps, bf16* __restrict__ Hn) {
+    const int m = blockIdx.x;
+    const int nvec = N >> 3;
+    uint4 xv[RN_MAXV];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < RN_MAXV; ++i) {
+        const int idx = threadIdx.x + i * RN_THREADS;
+        if (idx < nvec) {
+            const int c0 = idx * 8;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = 0.f;
+            for (int s = 0; s < splits; ++s) {
+                const float4* p = reinterpret_cast<const float4*>(ws + ((size_t)s * M + m) * N + c0);
+                const float4 a = p[0], b = p[1];
+                v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+            }
+            if (flags & TL_EPI_BIAS) {
+                const uint4 bb = *reinterpret_cast<const uint4*>(bias + c0);
+                const uint32_t* b32 = reinterpret_cast<const uint32_t*>(&bb);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { v[2 * j] += bf16_lo(b32[j]); v[2 * j + 1] += bf16_hi(b32[j]); }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = rbf(v[j]);
+            if (flags & TL_EPI_RESIDUAL) {
+                const uint4 rr = *reinterpret_cast<const uint4*>(residual + (size_t)m * ldr + c0);
+                const uint32_t* r32 = reinterpret_cast<const uint32_t*>(&rr);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { v[2 * j] += bf16_lo(r32[j]); v[2 * j + 1] += bf16_hi(r32[j]); }
+            }
+            xv[i] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            *reinterpret_cast<uint4*>(C + (size_t)m * ldc + c0) = xv[i];
+            const uint32_t* u = reinterpret_cast<const uint32_t*>(&xv[i]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float a = bf16_lo(u[j]), b = bf16_hi(u[j]);
+                ss += a * a + b * b;
+            }
+        }
+    }
+    __shared__ float red[RN_THREADS / 32];
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < RN_THREADS / 32; ++i) tot += red[i];
+    const float rstd = 1.0f / sqrtf(tot / (float)N + eps);
+#pragma unroll
+    for (int i = 0; i < RN_MAXV; ++i) {
+        const int idx = threadIdx.x + i * RN_THREADS;
+        if (idx < nvec) {
+            const uint4 wv = reinterpret_cast<const uint4*>(norm_w)[idx];
+            uint4 o;
+            const uint32_t* u = reinterpret_cast<const uint32_t*>(&xv[i]);
+            const uint32_t* g = reinterpret_cast<const uint32_t*>(&wv);
+            uint32_t* ou = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float a = rbf(bf16_lo(u[j]) * rstd), b = rbf(bf16_hi(u[j]) * rstd);
+                ou[j] = pack_bf16(bf16_lo(g[j]) * a, bf16_hi(g[j]) * b);
+            }
+            reinterpret_cast<uint4*>(Hn + (size_t)m * N)[idx] = o;
+        }
+    }
+}
+
 int gemm2_dispatch(bool a_mn, bool b_mn, const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
                    const void* bias, const void* residual, int flags, cudaStream_t st);
 
@@ -361,9 +438,25 @@ extern "C" int tl_gemm_bf16(const void* A, const void* B, void* C, int M, int N,
 
 // Same as tl_gemm_bf16; with a workspace the weight-streaming regime (M <= 128, K-major operands, too few output tiles to
 // occupy every SM) is split along K so that all SMs stream weights, then reduced with the epilogue applied once.
+extern "C" int tl_gemm_bf16_ws_norm(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
+                                    const void* bias, const void* residual, int flags, void* workspace, size_t ws_bytes,
+                                    const void* norm_w, float eps, void* H_out, void* stream);
+extern "C" int tl_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd_out, int rows, int H, float eps, void* stream);
+
 extern "C" int tl_gemm_bf16_ws(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
                                const void* bias, const void* residual, int flags, void* workspace, size_t ws_bytes, void* stream) {
+    return tl_gemm_bf16_ws_norm(A, B, C, M, N, K, lda, ldb, ldc, bias, residual, flags, workspace, ws_bytes, nullptr, 0.f, nullptr,
+                                stream);
+}
+
+// ... and, when norm_w != NULL, H_out[M,N] = RMSNorm(C) * norm_w (the norm that follows this Linear in the decoder layer):
+// fused into the split-K reduce pass when that path is taken, a separate tl_rmsnorm_fwd launch otherwise (same bits).
+extern "C" int tl_gemm_bf16_ws_norm(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
+                                    const void* bias, const void* residual, int flags, void* workspace, size_t ws_bytes,
+                                    const void* norm_w, float eps, void* H_out, void* stream) {
     using namespace tl;
+    TL_REQUIRE(!norm_w || (H_out && ldc == N && !(flags & (TL_EPI_SWIGLU | TL_EPI_OUT_F32 | TL_EPI_ACCUM))), TL_ERR_INVALID,
+               "tl_gemm_bf16_ws_norm: the fused norm needs H_out, ldc == N and a plain bf16 (bias/residual) epilogue");
     const int tiles_n = (N + 127) / 128, num_k = (K + BK - 1) / BK;
     const bool plain = !(flags & (TL_A_MN_MAJOR | TL_B_MN_MAJOR));
     if (workspace && plain && M > 0 && M <= BM && K % 8 == 0 && N % 8 == 0 && tiles_n * 2 <= sm_count() && num_k >= 16) {
@@ -379,13 +472,23 @@ extern "C" int tl_gemm_bf16_ws(const void* A, const void* B, void* C, int M, int
             int rc = launch_gemm<128, false, false>(A, B, workspace, M, N, K, lda, ldb, N, nullptr, nullptr, TL_EPI_OUT_F32, st,
                                                     splits, kb_per);
             if (rc != TL_OK) return rc;
+            if (norm_w && N <= RN_THREADS * RN_MAXV * 8) {
+                splitk_reduce_norm_kernel<<<M, RN_THREADS, 0, st>>>((const float*)workspace, (bf16*)C, M, N, ldc, splits,
+                                                                    (const bf16*)bias, (const bf16*)residual, ldc, flags,
+                                                                    (const bf16*)norm_w, eps, (bf16*)H_out);
+                return check_launch("tl_gemm_bf16_ws_norm (reduce + norm)");
+            }
             const long long items = (long long)M * (N >> 3);
             splitk_reduce_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>((const float*)workspace, C, M, N, ldc, splits,
                                                                                   (const bf16*)bias, (const bf16*)residual, ldc, flags);
-            return check_launch("tl_gemm_bf16_ws (reduce)");
+            int rc2 = check_launch("tl_gemm_bf16_ws (reduce)");
+            if (rc2 != TL_OK || !norm_w) return rc2;
+            return tl_rmsnorm_fwd(C, norm_w, H_out, nullptr, M, N, eps, stream);
         }
     }
-    return tl_gemm_bf16(A, B, C, M, N, K, lda, ldb, ldc, bias, residual, flags, stream);
+    int rc = tl_gemm_bf16(A, B, C, M, N, K, lda, ldb, ldc, bias, residual, flags, stream);
+    if (rc != TL_OK || !norm_w) return rc;
+    return tl_rmsnorm_fwd(C, norm_w, H_out, nullptr, M, N, eps, stream);
 }
 
 extern "C" int tl_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,

@@ -301,19 +301,23 @@ class CudaLayerGroup:
         nat.gemv(w.act, v[f"l{li}.wd"], out=x if out is None else out, residual=x, next_w=after)
 
     def _layer_decode_batched(self, j: int, x: torch.Tensor, B: int, w: ShardBuffers, out: Optional[torch.Tensor] = None):
-        """B > 8 single-token rows: tcgen05 GEMMs in the weight-streaming regime (split along K where a Linear has too
-        few output tiles to occupy every SM) + decode attention."""
+        """More single-token rows than the GEMV path takes: tcgen05 GEMMs in the weight-streaming regime (split along K
+        where a Linear has too few output tiles to occupy every SM) + decode attention.  The RMSNorm after each
+        residual Linear rides in that Linear's split-K reduce pass, so layer j > 0 finds its normalised input in w.h."""
         cfg, v, li = self.cfg, self.p.v, self.layer_ids[j]
         ws = self.gemm_ws if B <= 128 else None
-        nat.rmsnorm_fwd(x, v[f"l{li}.ln1"], cfg.rms_eps, out=w.h)
+        if j == 0:
+            nat.rmsnorm_fwd(x, v[f"l{li}.ln1"], cfg.rms_eps, out=w.h)
         nat.gemm(w.h, v[f"l{li}.wqkv"], out=w.qkv, bias=v.get(f"l{li}.bqkv"), ws=ws)
         self._decode_attention(j, li, B, w)
-        nat.gemm(w.attn, v[f"l{li}.wo"], out=x, residual=x, ws=ws)
-        nat.rmsnorm_fwd(x, v[f"l{li}.ln2"], cfg.rms_eps, out=w.h)
+        nat.gemm(w.attn, v[f"l{li}.wo"], out=x, residual=x, ws=ws, norm_w=v[f"l{li}.ln2"], eps=cfg.rms_eps, h_out=w.h)
         nat.gemm(w.h, v[f"l{li}.wgu"], out=w.act, flags=nat.EPI_SWIGLU, ws=ws)
-        nat.gemm(w.act, v[f"l{li}.wd"], out=x if out is None else out, residual=x, ws=ws)
+        if j + 1 < self.num_layers:
+            nat.gemm(w.act, v[f"l{li}.wd"], out=x, residual=x, ws=ws, norm_w=v[f"l{self.layer_ids[j + 1]}.ln1"],
+                     eps=cfg.rms_eps, h_out=w.h)
+        else:
+            nat.gemm(w.act, v[f"l{li}.wd"], out=x if out is None else out, residual=x, ws=ws)
 
-    # ------------------------------------------------------------------------------------------ shard passes
     def prefill(self, hidden: torch.Tensor, past_len: int = 0) -> torch.Tensor:
         """hidden [B,S,H] -> [B,S,H]; appends S positions to the KV cache starting at ``past_len``."""
         B, S, H = hidden.shape

@@ -171,7 +171,9 @@ class CudaStage:
         if self._use_step_kernel(B):
             return 1
         fused = self.slots[0].T_max <= self.slots[0].FUSED_DECODE_MAX_T
-        n = len(self.slots[0].layer_ids) * ((7 if B <= gemv_max_rows() else 9) - (2 if fused else 0)) + 2
+        gemv = B <= gemv_max_rows()
+        # GEMV path: 4 Linears + attention (1 fused / 3); batched: 4 GEMMs + 3 split-K reduce(+norm) passes + attention
+        n = len(self.slots[0].layer_ids) * ((7 if gemv else 10) - (2 if fused else 0)) + 2 + (0 if gemv else 1)
         if ring:
             n += 3 if self.has_embed else 2          # wait (+ token log) + signal
         if self.has_embed:

@@ -33,6 +33,8 @@ _SIGS = {
     "tl_gemm_splitk_ws": (c_size_t, [c_int, c_int]),
     "tl_gemm_bf16_ws": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "tl_gemm_bf16_ws_norm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                     c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_float, c_void_p, c_void_p]),
     "tl_gemv_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                              c_float, c_int, c_void_p]),
     "tl_gemv_bf16_pf": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
@@ -188,7 +190,8 @@ def gemm_splitk_ws(M: int, N: int) -> int:
 
 def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *, bias=None, residual=None,
          flags: int = 0, M: Optional[int] = None, N: Optional[int] = None, K: Optional[int] = None,
-         ws: Optional[torch.Tensor] = None) -> torch.Tensor:
+         ws: Optional[torch.Tensor] = None, norm_w: Optional[torch.Tensor] = None, eps: float = 1e-6,
+         h_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """C[M,N] = A·B^T with the epilogue ``flags``.  A is [M,K] (or [K,M] with A_MN_MAJOR), B is [N,K] (or [K,N])."""
     require_device()
     _bf16(a, b, bias, residual)
@@ -206,6 +209,12 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
         flags |= EPI_BIAS
     if residual is not None:
         flags |= EPI_RESIDUAL
+    if norm_w is not None:          # also h_out = RMSNorm(out) * norm_w (fused into the split-K reduce when that path runs)
+        assert h_out is not None and h_out.dtype == torch.bfloat16 and h_out.is_contiguous() and h_out.shape == out.shape
+        _check(load().tl_gemm_bf16_ws_norm(_p(a), _p(b), _p(out), M, N, K, a.stride(0), b.stride(0), out.stride(0), _p(bias),
+                                           _p(residual), flags, _p(ws), 0 if ws is None else ws.numel() * ws.element_size(),
+                                           _p(norm_w), eps, _p(h_out), _stream()), "tl_gemm_bf16_ws_norm")
+        return out
     if ws is not None:
         _check(load().tl_gemm_bf16_ws(_p(a), _p(b), _p(out), M, N, K, a.stride(0), b.stride(0), out.stride(0), _p(bias),
                                       _p(residual), flags, _p(ws), ws.numel() * ws.element_size(), _stream()),
