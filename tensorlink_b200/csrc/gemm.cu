@@ -361,10 +361,24 @@ splitk_reduce_norm_kernel(const float* __restrict__ ws, bf16* __restrict__ C, in
             float v[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = 0.f;
-            for (int s = 0; s < splits; ++s) {
-                const float4* p = reinterpret_cast<const float4*>(ws + ((size_t)s * M + m) * N + c0);
-                const float4 a = p[0], b = p[1];
-                v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+            // all partial loads of this column group are issued before the first add (one CTA serves a whole row, so
+            // memory-level parallelism per thread is what keeps this pass short); summed in split order like the
+            // stand-alone reduce kernel
+            float4 pa[8], pb[8];
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                if (s < splits) {
+                    const float4* p = reinterpret_cast<const float4*>(ws + ((size_t)s * M + m) * N + c0);
+                    pa[s] = __ldcs(p);
+                    pb[s] = __ldcs(p + 1);
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                if (s < splits) {
+                    v[0] += pa[s].x; v[1] += pa[s].y; v[2] += pa[s].z; v[3] += pa[s].w;
+                    v[4] += pb[s].x; v[5] += pb[s].y; v[6] += pb[s].z; v[7] += pb[s].w;
+                }
             }
             if (flags & TL_EPI_BIAS) {
                 const uint4 bb = *reinterpret_cast<const uint4*>(bias + c0);
