@@ -13,7 +13,9 @@ pytestmark = pytest.mark.gpu
 
 def _run(cfg, B, prompt, new, impl, **kw):
     from tensorlink_b200.ml import DistributedModel
+    from tensorlink_b200.ml import shard
     os.environ["TL_DECODE_IMPL"] = impl
+    saved, shard._GEMV_MAX_ROWS = shard._GEMV_MAX_ROWS, 8      # the step kernel restates the GEMV launch sequence (rows <= 4)
     try:
         dm = DistributedModel(cfg, training=False, max_batch=B, max_seq=prompt + new + 3, **kw)
         ids = synthetic_tokens(cfg, B, prompt)
@@ -22,6 +24,7 @@ def _run(cfg, B, prompt, new, impl, **kw):
         return out, st.logits_dec[:B].cpu().clone(), [k.cpu().clone() for k in st.slots[0].kc], st.n_decode_launches(B)
     finally:
         os.environ.pop("TL_DECODE_IMPL", None)
+        shard._GEMV_MAX_ROWS = saved
 
 
 @pytest.mark.parametrize("cfg", [C.TINY_QWEN2, C.TINY_QWEN2_D128, C.TINY_QWEN3], ids=lambda c: c.name)
@@ -54,5 +57,6 @@ def test_step_kernel_repeated_launches_leave_sync_clean():
         z = dm.generate(ids, max_new_tokens=30, use_graph=False).cpu()
     finally:
         os.environ.pop("TL_DECODE_IMPL", None)
+        shard._GEMV_MAX_ROWS = saved
     assert torch.equal(x, y) and torch.equal(x, z)
     assert int(dm.stage.step_ws[:8].view(torch.int32).abs().sum()) == 0
