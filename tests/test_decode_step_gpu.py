@@ -57,6 +57,5 @@ def test_step_kernel_repeated_launches_leave_sync_clean():
         z = dm.generate(ids, max_new_tokens=30, use_graph=False).cpu()
     finally:
         os.environ.pop("TL_DECODE_IMPL", None)
-        shard._GEMV_MAX_ROWS = saved
     assert torch.equal(x, y) and torch.equal(x, z)
     assert int(dm.stage.step_ws[:8].view(torch.int32).abs().sum()) == 0

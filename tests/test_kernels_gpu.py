@@ -417,7 +417,7 @@ def test_peer_wait_signal_put(nat):
                                         (200, 1024, 2048, "res")])
 def test_gemm_with_fused_following_rmsnorm(nat, M, N, K, mode):
     """tl_gemm_bf16_ws_norm: C as tl_gemm_bf16_ws, plus H = RMSNorm(C) * g — fused into the split-K reduce (decode shapes)
-    or a separate launch (no split / M > 128); either way identical to running tl_rmsnorm_fwd on C."""
+    or a separate launch (no split / M > 128); C is identical, H equals tl_rmsnorm_fwd(C) up to the reduction order."""
     a, w = rnd(M, K, seed=51), rnd(N, K, seed=52, std=0.05)
     g = (1 + 0.1 * torch.randn(N)).bfloat16()
     ws = torch.empty(nat.gemm_splitk_ws(min(M, 128), N), dtype=torch.uint8, device="cuda")
@@ -426,7 +426,7 @@ def test_gemm_with_fused_following_rmsnorm(nat, M, N, K, mode):
     h_ref = nat.rmsnorm_fwd(c_ref, dev(g), 1e-6)
     h = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
     c = nat.gemm(dev(a), dev(w), ws=ws, norm_w=dev(g), eps=1e-6, h_out=h, **kw)
-    assert torch.equal(c, c_ref) and torch.equal(h, h_ref)
+    assert torch.equal(c, c_ref) and O.rel_l2(h.cpu(), h_ref.cpu()) <= 1e-4      # (sum of squares reduced in another order)
     ref = F.linear(a, w, kw.get("bias").cpu() if mode == "bias" else None)
     if mode == "res":
         ref = kw["residual"].cpu() + ref
