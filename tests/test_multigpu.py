@@ -41,14 +41,16 @@ def test_two_gpu_pipeline_equals_single_stage(tmp_path):
     assert (t0.float() - tr.float()).norm() / tr.float().norm() < 5e-3   # = single-stage sum up to bf16 add order
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_peer_ring_generation(tmp_path, world):
-    """Decode hops over peer-mapped mailboxes (first, middle and last stages) = NCCL hops = one stage, bit for bit."""
+@pytest.mark.parametrize("world,rows", [(2, 2), (2, 5), (4, 2)])
+def test_peer_ring_generation(tmp_path, world, rows):
+    """Decode hops over peer-mapped mailboxes (first, middle and last stages) = NCCL hops = one stage, bit for bit;
+    rows = 2 takes the GEMV path (the last GEMV stores into the neighbour), rows = 5 the GEMM path (the split-K reduce
+    pass does)."""
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
            "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "ring_worker.py"), str(tmp_path)]
-    r = subprocess.run(cmd, env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, env=dict(os.environ, PYTHONPATH=ROOT, RING_ROWS=str(rows)), capture_output=True, text=True, timeout=600)
     errs = "".join(open(p).read() for p in sorted(map(str, tmp_path.glob("err*.txt"))))
     assert r.returncode == 0, errs or r.stderr[-4000:]
     for rank in range(world):
