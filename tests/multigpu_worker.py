@@ -19,7 +19,8 @@ def main(out_dir):
     rank, world = dist.get_rank(), dist.get_world_size()
     cfg = C.TINY_QWEN2_D128
     res = {}
-    single = DistributedModel(cfg, training=False, max_batch=4, max_seq=96, link=StageLink(0, 1)) if rank == 0 else None
+    # same micro-batching as the pipeline (2 x 2 rows), so the same kernels run on the same shapes
+    single = DistributedModel(cfg, training=False, n_pipelines=2, max_batch=4, max_seq=96, link=StageLink(0, 1)) if rank == 0 else None
     dm = DistributedModel(cfg, training=False, n_pipelines=2, max_batch=4, max_seq=96)
     ids = synthetic_tokens(cfg, 4, 20).cuda()
     out = dm(ids if rank == 0 else None, gather_logits=True)
@@ -27,7 +28,6 @@ def main(out_dir):
     gen_ng = dm.generate(ids if rank == 0 else None, max_new_tokens=24, use_graph=False)
     if rank == 0:
         ref_logits = single(ids).logits
-        single.n_pipelines = 1
         ref_gen = single.generate(ids, max_new_tokens=24)
         res["logits_equal"] = bool(torch.equal(out.logits, ref_logits))
         res["gen_equal"] = bool(torch.equal(gen, ref_gen))
