@@ -32,14 +32,14 @@ def main(out_dir):
     res["peer_vs_nccl"] = bool(torch.equal(gen, gen_nccl))
     res["wait_ms"] = float(dm._ring.wait_ns.item()) * 1e-6 if res["used_ring"] else None
     if rank == 0:
-        single = DistributedModel(cfg, training=False, n_pipelines=1, max_batch=rows * world, max_seq=96, link=StageLink(0, 1))
+        single = DistributedModel(cfg, training=False, n_pipelines=world, max_batch=rows * world, max_seq=96, link=StageLink(0, 1))
         res["vs_single"] = bool(torch.equal(gen, single.generate(ids, max_new_tokens=40)))
     # checkpoint out of the sharded job (one safetensors file per stage + index), back into a single stage
     ck = os.path.join(out_dir, "ckpt")
     dm.save_pretrained(ck)
     res["ckpt_files"] = sorted(f for f in os.listdir(ck) if f.endswith(".safetensors"))
     if rank == 0:
-        again = DistributedModel(ck, training=False, n_pipelines=1, max_batch=rows * world, max_seq=96, link=StageLink(0, 1), seed=5)
+        again = DistributedModel(ck, training=False, n_pipelines=world, max_batch=rows * world, max_seq=96, link=StageLink(0, 1), seed=5)
         res["ckpt_roundtrip"] = bool(torch.equal(gen, again.generate(ids, max_new_tokens=40)))
     torch.save(res, os.path.join(out_dir, f"ring{rank}.pt"))
     dist.barrier()
