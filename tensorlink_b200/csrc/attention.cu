@@ -364,6 +364,11 @@ __global__ void attn_decode_reduce_kernel(const float* __restrict__ ws, bf16* __
 
 }  // namespace tl
 
+namespace tl {
+int attn_prefill_tc_dispatch(const void* q, const void* k_cache, const void* v_cache, void* out, float* lse, int B, int S,
+                             int past_len, int n_h, int n_kv, int d, int T_max, float scale, cudaStream_t st);
+}
+
 extern "C" {
 
 int tl_attn_prefill_fwd(const void* q, const void* k_cache, const void* v_cache, void* out, float* lse, int B, int S,
@@ -374,9 +379,17 @@ int tl_attn_prefill_fwd(const void* q, const void* k_cache, const void* v_cache,
     TL_REQUIRE(past_len >= 0 && past_len + S <= T_max, TL_ERR_INVALID,
                "tl_attn_prefill_fwd: past_len %d + S %d exceeds cache T_max %d", past_len, S, T_max);
     if (B == 0 || S == 0) return TL_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    {   // tcgen05 tiles (attention_tc.cu) from one full 128-row query tile upwards; TL_ATTN_IMPL=mma|tc forces a path
+        const char* e = getenv("TL_ATTN_IMPL");          // read per call: tests flip it
+        const int impl = !e ? 0 : (e[0] == 'm' ? 1 : (e[0] == 't' ? 2 : 0));
+        if (impl == 2 || (impl == 0 && S >= 128)) {
+            const int rc = attn_prefill_tc_dispatch(q, k_cache, v_cache, out, lse, B, S, past_len, n_h, n_kv, d, T_max, scale, st);
+            if (rc != 1) return rc;
+        }
+    }
     const dim3 grid((S + FA_BQ - 1) / FA_BQ, n_h, B);
     const float sl2 = scale * 1.4426950408889634f;
-    cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = (size_t)(FA_BQ + 4 * FA_BKV) * (d + 8) * sizeof(bf16);
     if (d == 64) {
         static bool done = false;

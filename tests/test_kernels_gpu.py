@@ -270,14 +270,19 @@ def _attn_case(B, S, past, n_h, n_kv, d, seed, std=1.0):
     return q, k, v, ref, f32
 
 
+@pytest.mark.parametrize("impl", ["mma", "tc"])
 @pytest.mark.parametrize("B,S,past,n_h,n_kv,d", [(2, 100, 0, 4, 2, 64), (1, 64, 0, 14, 2, 64), (1, 50, 37, 4, 2, 128),
-                                                 (2, 257, 0, 8, 2, 128), (1, 1, 200, 4, 4, 64), (1, 130, 300, 7, 1, 128)])
-def test_attn_prefill(nat, B, S, past, n_h, n_kv, d):
+                                                 (2, 257, 0, 8, 2, 128), (1, 1, 200, 4, 4, 64), (1, 130, 300, 7, 1, 128),
+                                                 (1, 512, 0, 28, 4, 128), (2, 300, 100, 14, 2, 64), (1, 1024, 0, 4, 2, 128)])
+def test_attn_prefill(nat, monkeypatch, impl, B, S, past, n_h, n_kv, d):
+    """Both prefill kernels: legacy mma.sync tiles (attention.cu) and the tcgen05 / TMEM kernel (attention_tc.cu)."""
+    monkeypatch.setenv("TL_ATTN_IMPL", impl)
     q, k, v, ref, f32 = _attn_case(B, S, past, n_h, n_kv, d, seed=30)
     T_max = past + S + 19
     kc = torch.zeros(B, n_kv, T_max, d, dtype=torch.bfloat16)
     vc = torch.zeros_like(kc)
     kc[:, :, :past + S], vc[:, :, :past + S] = k, v
+    kc[:, :, past + S:], vc[:, :, past + S:] = 40.0, -30.0      # poison: keys beyond the valid length must be ignored
     out = torch.empty(B, S, n_h * d, dtype=torch.bfloat16, device="cuda")
     lse = torch.empty(B, n_h, S, dtype=torch.float32, device="cuda")
     nat.attn_prefill_fwd(dev(q), dev(kc), dev(vc), out, lse, B, S, past, n_h, n_kv, d, d ** -0.5)
