@@ -20,16 +20,23 @@
 
 namespace tl {
 
-constexpr int TC_BQ = 128, TC_BKV = 128;
+constexpr int TC_BQ = 128;
 constexpr int TC_THREADS = 160;                 // 4 softmax warps + 1 control warp
 
-template <int D>
+// BKV = 128: one CTA per SM (192 KB of shared memory at D = 128, 512 TMEM columns).
+// BKV = 64:  112 KB and 256 TMEM columns, so TWO CTAs share an SM: while one CTA's softmax warps work (one warp per
+//            scheduler cannot hide its own TMEM / SFU latencies) the other CTA's MMAs and softmax fill the gaps.
+template <int D, int BKV>
 struct TcCfg {
-    static constexpr int TILE_BYTES = 128 * D * 2;                  // Q, K or V tile
-    static constexpr int P_BYTES = 128 * 128 * 2;
-    static constexpr int SMEM_BYTES = TILE_BYTES * 5 + P_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-    static constexpr uint32_t TMEM_COLS = 512;
-    static constexpr uint32_t COL_S0 = 0, COL_S1 = 128, COL_O = 256;
+    static constexpr int Q_BYTES = 128 * D * 2;
+    static constexpr int KV_BYTES = BKV * D * 2;                    // one K or V tile
+    static constexpr int P_BYTES = 128 * BKV * 2;
+    // no alignment slack: two CTAs of 112 KB + barriers + the 1 KB the system reserves per CTA must fit in 228 KB; the
+    // dynamic segment is declared 1024-byte aligned (the kernel has no static shared memory) and the kernel traps if not
+    static constexpr int SMEM_BYTES = Q_BYTES + 4 * KV_BYTES + P_BYTES + 256 /*barriers*/;
+    static constexpr uint32_t TMEM_COLS = (BKV == 128) ? 512 : 256;
+    static constexpr uint32_t COL_S0 = 0, COL_S1 = BKV, COL_O = 2 * BKV;
+    static constexpr int CTAS_PER_SM = (BKV == 128) ? 1 : 2;
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -38,19 +45,22 @@ __device__ __forceinline__ float fast_exp2(float x) {
     return y;
 }
 
-template <int D>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int D, int BKV>
+__global__ void __launch_bounds__(TC_THREADS, TcCfg<D, BKV>::CTAS_PER_SM)
 attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ out, float* __restrict__ lse, int S, int past_len,
                        int n_h, int n_kv, int T_max, float scale_log2) {
-    using Cfg = TcCfg<D>;
+    using Cfg = TcCfg<D, BKV>;
     constexpr int DB = D / 64;                                       // 64-element blocks along the head dimension
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int KB = BKV / 64;                                     // 64-key blocks per KV tile
+    constexpr int TC_BKV = BKV;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    if (smem_u32(smem_raw) & 1023u) __trap();                        // swizzled tiles need a 1024-byte aligned base
+    unsigned char* smem = smem_raw;
     unsigned char* sQ = smem;
-    unsigned char* sK = sQ + Cfg::TILE_BYTES;                        // [2][TILE]
-    unsigned char* sV = sK + 2 * Cfg::TILE_BYTES;                    // [2][TILE]
-    unsigned char* sP = sV + 2 * Cfg::TILE_BYTES;                    // [2 key blocks][128 rows][128 B]
+    unsigned char* sK = sQ + Cfg::Q_BYTES;                           // [2][KV tile]: [D/64 blocks][BKV keys][128 B]
+    unsigned char* sV = sK + 2 * Cfg::KV_BYTES;                      // [2][KV tile]: [key block][D/64 blocks][64 keys][128 B]
+    unsigned char* sP = sV + 2 * Cfg::KV_BYTES;                      // [key block][128 rows][128 B]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
     uint64_t* bar_q = bars;            // 1
     uint64_t* bar_k = bars + 1;        // 2
@@ -103,19 +113,19 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         if (lane == 0) {
             auto load_kv = [&](int j) {
                 const int u = j & 1;
-                mbar_expect_tx(&bar_k[u], Cfg::TILE_BYTES);
+                mbar_expect_tx(&bar_k[u], Cfg::KV_BYTES);
 #pragma unroll
                 for (int db = 0; db < DB; ++db)
-                    tma_load_2d(sK + u * Cfg::TILE_BYTES + db * 16384, &tmK, &bar_k[u], 64 * db, kv_row0 + j * TC_BKV);
-                mbar_expect_tx(&bar_v[u], Cfg::TILE_BYTES);
+                    tma_load_2d(sK + u * Cfg::KV_BYTES + db * (BKV * 128), &tmK, &bar_k[u], 64 * db, kv_row0 + j * TC_BKV);
+                mbar_expect_tx(&bar_v[u], Cfg::KV_BYTES);
 #pragma unroll
-                for (int kb = 0; kb < 2; ++kb)
+                for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
                     for (int nb = 0; nb < DB; ++nb)
-                        tma_load_2d(sV + u * Cfg::TILE_BYTES + (kb * DB + nb) * 8192, &tmV, &bar_v[u], 64 * nb,
+                        tma_load_2d(sV + u * Cfg::KV_BYTES + (kb * DB + nb) * 8192, &tmV, &bar_v[u], 64 * nb,
                                     kv_row0 + j * TC_BKV + 64 * kb);
             };
-            constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0u, 0u);
+            constexpr uint32_t idesc_s = make_idesc_bf16(128, BKV, 0u, 0u);
             constexpr uint32_t idesc_o = make_idesc_bf16(128, D, 0u, 1u);
             auto issue_s = [&](int j) {
                 const int u = j & 1;
@@ -124,17 +134,18 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + (u ? Cfg::COL_S1 : Cfg::COL_S0);
                 const uint64_t da = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
-                const uint64_t dbk = make_smem_desc_sw128(smem_u32(sK + u * Cfg::TILE_BYTES), 16, 1024);
+                const uint64_t dbk = make_smem_desc_sw128(smem_u32(sK + u * Cfg::KV_BYTES), 16, 1024);
 #pragma unroll
                 for (int db = 0; db < DB; ++db)
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const uint64_t off = (uint64_t)((db * 16384 + 32 * k) >> 4);
-                        umma_bf16(d_tmem, da + off, dbk + off, idesc_s, (db | k) ? 1u : 0u);
+                        const uint64_t offq = (uint64_t)((db * 16384 + 32 * k) >> 4);
+                        const uint64_t offk = (uint64_t)((db * (BKV * 128) + 32 * k) >> 4);
+                        umma_bf16(d_tmem, da + offq, dbk + offk, idesc_s, (db | k) ? 1u : 0u);
                     }
                 umma_commit(&bar_s[u]);
             };
-            mbar_expect_tx(bar_q, Cfg::TILE_BYTES);
+            mbar_expect_tx(bar_q, Cfg::Q_BYTES);
 #pragma unroll
             for (int db = 0; db < DB; ++db) tma_load_2d(sQ + db * 16384, &tmQ, bar_q, h * D + 64 * db, b * S + q0);
             load_kv(0);
@@ -149,9 +160,9 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                 if (j >= 1) mbar_wait(bar_ofree, (uint32_t)(j - 1) & 1u);
                 tcgen05_fence_after();
                 const uint64_t dp = make_smem_desc_sw128(smem_u32(sP), 16, 1024);
-                const uint64_t dv = make_smem_desc_sw128(smem_u32(sV + u * Cfg::TILE_BYTES), 8192, 1024);
+                const uint64_t dv = make_smem_desc_sw128(smem_u32(sV + u * Cfg::KV_BYTES), 8192, 1024);
 #pragma unroll
-                for (int kb = 0; kb < 2; ++kb)
+                for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t pa = dp + (uint64_t)((kb * 16384 + 32 * k) >> 4);
@@ -179,7 +190,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 
         for (int j = 0; j < n_tiles; ++j) {
             const int u = j & 1;
-            const uint32_t ts = tmem_base + lane_base + (u ? TcCfg<D>::COL_S1 : TcCfg<D>::COL_S0);
+            const uint32_t ts = tmem_base + lane_base + (u ? Cfg::COL_S1 : Cfg::COL_S0);
             const int k0 = j * TC_BKV;
             const bool need_mask = (k0 + TC_BKV - 1 > past_len + q0) || (k0 + TC_BKV > T);   // warp-uniform
             mbar_wait(&bar_s[u], (uint32_t)(j >> 1) & 1u);
@@ -187,7 +198,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             // ---- pass A: row maximum
             float mx = -INFINITY;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < BKV / 32; ++c) {
                 uint32_t r[32];
                 tmem_ld32(ts + c * 32, r);
                 tmem_ld_wait();
@@ -208,7 +219,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             // ---- pass B: p = exp2(s * scale_log2 - m), P tile (bf16) to shared memory, row sum
             float rs = 0.f;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < BKV / 32; ++c) {
                 uint32_t r[32];
                 tmem_ld32(ts + c * 32, r);
                 tmem_ld_wait();
@@ -241,7 +252,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 #pragma unroll
             for (int c = 0; c < D / 32; ++c) {
                 uint32_t r[32];
-                tmem_ld32(tmem_base + lane_base + TcCfg<D>::COL_O + c * 32, r);
+                tmem_ld32(tmem_base + lane_base + Cfg::COL_O + c * 32, r);
                 tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 32; ++i) o[c * 32 + i] = o[c * 32 + i] * alpha + __uint_as_float(r[i]);
@@ -269,18 +280,18 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     }
 }
 
-template <int D>
+template <int D, int BKV>
 static int launch_tc(const void* q, const void* k_cache, const void* v_cache, void* out, float* lse, int B, int S, int past_len,
                      int n_h, int n_kv, int T_max, float scale, cudaStream_t st) {
-    using Cfg = TcCfg<D>;
+    using Cfg = TcCfg<D, BKV>;
     CUtensorMap tmQ, tmK, tmV;
     int rc = make_tensor_map(&tmQ, q, (uint64_t)n_h * D, (uint64_t)B * S, (uint64_t)n_h * D, 64, 128);
     if (rc != TL_OK) return rc;
-    rc = make_tensor_map(&tmK, k_cache, (uint64_t)D, (uint64_t)B * n_kv * T_max, (uint64_t)D, 64, 128);
+    rc = make_tensor_map(&tmK, k_cache, (uint64_t)D, (uint64_t)B * n_kv * T_max, (uint64_t)D, 64, BKV);
     if (rc != TL_OK) return rc;
     rc = make_tensor_map(&tmV, v_cache, (uint64_t)D, (uint64_t)B * n_kv * T_max, (uint64_t)D, 64, 64);
     if (rc != TL_OK) return rc;
-    auto kern = attn_prefill_tc_kernel<D>;
+    auto kern = attn_prefill_tc_kernel<D, BKV>;
     static bool attr_done = false;
     if (!attr_done) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
@@ -297,8 +308,12 @@ static int launch_tc(const void* q, const void* k_cache, const void* v_cache, vo
 int attn_prefill_tc_dispatch(const void* q, const void* k_cache, const void* v_cache, void* out, float* lse, int B, int S,
                              int past_len, int n_h, int n_kv, int d, int T_max, float scale, cudaStream_t st) {
     if ((((uintptr_t)q | (uintptr_t)k_cache | (uintptr_t)v_cache | (uintptr_t)out) & 15) != 0) return 1;
-    if (d == 128) return launch_tc<128>(q, k_cache, v_cache, out, lse, B, S, past_len, n_h, n_kv, T_max, scale, st);
-    if (d == 64) return launch_tc<64>(q, k_cache, v_cache, out, lse, B, S, past_len, n_h, n_kv, T_max, scale, st);
+    const char* e = getenv("TL_ATTN_BKV");                  // 64 (default: two CTAs per SM) or 128
+    const bool wide = e && e[0] == '1';
+    if (d == 128) return wide ? launch_tc<128, 128>(q, k_cache, v_cache, out, lse, B, S, past_len, n_h, n_kv, T_max, scale, st)
+                              : launch_tc<128, 64>(q, k_cache, v_cache, out, lse, B, S, past_len, n_h, n_kv, T_max, scale, st);
+    if (d == 64) return wide ? launch_tc<64, 128>(q, k_cache, v_cache, out, lse, B, S, past_len, n_h, n_kv, T_max, scale, st)
+                             : launch_tc<64, 64>(q, k_cache, v_cache, out, lse, B, S, past_len, n_h, n_kv, T_max, scale, st);
     return 1;
 }
 
