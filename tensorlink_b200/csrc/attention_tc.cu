@@ -195,53 +195,83 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             const bool need_mask = (k0 + TC_BKV - 1 > past_len + q0) || (k0 + TC_BKV > T);   // warp-uniform
             mbar_wait(&bar_s[u], (uint32_t)(j >> 1) & 1u);
             tcgen05_fence_after();
-            // ---- pass A: row maximum
-            float mx = -INFINITY;
-#pragma unroll
-            for (int c = 0; c < BKV / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld32(ts + c * 32, r);
+            float mx = -INFINITY, rs = 0.f;
+            float m_new, m_use, alpha;
+            if constexpr (BKV == 64) {
+                // ---- one pass: the whole score row (64 fp32) stays in registers; both TMEM loads are issued before the wait
+                uint32_t r[64];
+                tmem_ld32(ts, r);
+                tmem_ld32(ts + 32, r + 32);
                 tmem_ld_wait();
-                if (need_mask) {
+                tcgen05_fence_before();
+                mbar_arrive(&bar_sfree[u]);                           // S[u] may be overwritten by S_{j+2}
+#pragma unroll
+                for (int i = 0; i < 64; ++i) {
+                    const int kp = k0 + i;
+                    if (need_mask && !(kp <= qpos && kp < T)) r[i] = __float_as_uint(-INFINITY);
+                    mx = fmaxf(mx, __uint_as_float(r[i]));
+                }
+                m_new = fmaxf(m_run, mx * scale_log2);
+                m_use = (m_new == -INFINITY) ? 0.f : m_new;           // fully masked so far (rows beyond S): keep p = 0
+                alpha = (m_run == -INFINITY) ? 0.f : fast_exp2(m_run - m_use);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {                         // eight 16-byte chunks (8 keys each)
+                    float p[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        p[i] = fast_exp2(__uint_as_float(r[8 * q + i]) * scale_log2 - m_use);   // exp2(-inf) = 0 for masked keys
+                        rs += p[i];
+                    }
+                    *reinterpret_cast<uint4*>(prow + ((q ^ sw) << 4)) =
+                        make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
+                }
+            } else {
+                // ---- pass A: row maximum
+#pragma unroll
+                for (int c = 0; c < BKV / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(ts + c * 32, r);
+                    tmem_ld_wait();
+                    if (need_mask) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const int kp = k0 + c * 32 + i;
+                            if (kp <= qpos && kp < T) mx = fmaxf(mx, __uint_as_float(r[i]));
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+                    }
+                }
+                m_new = fmaxf(m_run, mx * scale_log2);
+                m_use = (m_new == -INFINITY) ? 0.f : m_new;
+                alpha = (m_run == -INFINITY) ? 0.f : fast_exp2(m_run - m_use);
+                // ---- pass B: p = exp2(s * scale_log2 - m), P tile (bf16) to shared memory, row sum
+#pragma unroll
+                for (int c = 0; c < BKV / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(ts + c * 32, r);
+                    tmem_ld_wait();
+                    float p[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         const int kp = k0 + c * 32 + i;
-                        if (kp <= qpos && kp < T) mx = fmaxf(mx, __uint_as_float(r[i]));
+                        const bool ok = !need_mask || (kp <= qpos && kp < T);
+                        p[i] = ok ? fast_exp2(__uint_as_float(r[i]) * scale_log2 - m_use) : 0.f;
+                        rs += p[i];
                     }
-                } else {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+                    for (int q = 0; q < 4; ++q) {                     // four 16-byte chunks (8 keys each)
+                        const int cc = c * 4 + q;                     // chunk index 0..15 within the row
+                        const int kb = cc >> 3, within = cc & 7;
+                        *reinterpret_cast<uint4*>(prow + kb * 16384 + ((within ^ sw) << 4)) =
+                            make_uint4(pack_bf16(p[8 * q], p[8 * q + 1]), pack_bf16(p[8 * q + 2], p[8 * q + 3]),
+                                       pack_bf16(p[8 * q + 4], p[8 * q + 5]), pack_bf16(p[8 * q + 6], p[8 * q + 7]));
+                    }
                 }
+                tcgen05_fence_before();
+                mbar_arrive(&bar_sfree[u]);                           // S[u] may be overwritten by S_{j+2}
             }
-            const float m_new = fmaxf(m_run, mx * scale_log2);
-            const float m_use = (m_new == -INFINITY) ? 0.f : m_new;  // fully masked so far (rows beyond S): keep p = 0
-            const float alpha = (m_run == -INFINITY) ? 0.f : fast_exp2(m_run - m_use);
-            // ---- pass B: p = exp2(s * scale_log2 - m), P tile (bf16) to shared memory, row sum
-            float rs = 0.f;
-#pragma unroll
-            for (int c = 0; c < BKV / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld32(ts + c * 32, r);
-                tmem_ld_wait();
-                float p[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int kp = k0 + c * 32 + i;
-                    const bool ok = !need_mask || (kp <= qpos && kp < T);
-                    p[i] = ok ? fast_exp2(__uint_as_float(r[i]) * scale_log2 - m_use) : 0.f;
-                    rs += p[i];
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {                         // four 16-byte chunks (8 keys each)
-                    const int cc = c * 4 + q;                         // chunk index 0..15 within the row
-                    const int kb = cc >> 3, within = cc & 7;
-                    *reinterpret_cast<uint4*>(prow + kb * 16384 + ((within ^ sw) << 4)) =
-                        make_uint4(pack_bf16(p[8 * q], p[8 * q + 1]), pack_bf16(p[8 * q + 2], p[8 * q + 3]),
-                                   pack_bf16(p[8 * q + 4], p[8 * q + 5]), pack_bf16(p[8 * q + 6], p[8 * q + 7]));
-                }
-            }
-            tcgen05_fence_before();
-            mbar_arrive(&bar_sfree[u]);                               // S[u] may be overwritten by S_{j+2}
             fence_proxy_async();                                      // P stores -> visible to the tensor core's reads
             mbar_arrive(bar_p);
             l_run = l_run * alpha + rs;
