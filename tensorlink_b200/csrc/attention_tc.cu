@@ -197,8 +197,10 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             tcgen05_fence_after();
             float mx = -INFINITY, rs = 0.f;
             float m_new, m_use, alpha;
-            if constexpr (BKV == 64) {
-                // ---- one pass: the whole score row (64 fp32) stays in registers; both TMEM loads are issued before the wait
+            if constexpr (BKV == 64 && D == 64) {
+                // ---- one pass: the whole score row (64 fp32) stays in registers beside the 64 output accumulators; both
+                // TMEM loads are issued before the wait.  (At D = 128 the extra 64 registers spill: 292 vs 319 TFLOP/s at
+                // S = 4096, so that case keeps the two-pass form below.)
                 uint32_t r[64];
                 tmem_ld32(ts, r);
                 tmem_ld32(ts + 32, r + 32);
