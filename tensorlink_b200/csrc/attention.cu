@@ -367,6 +367,8 @@ __global__ void attn_decode_reduce_kernel(const float* __restrict__ ws, bf16* __
 namespace tl {
 int attn_prefill_tc_dispatch(const void* q, const void* k_cache, const void* v_cache, void* out, float* lse, int B, int S,
                              int past_len, int n_h, int n_kv, int d, int T_max, float scale, cudaStream_t st);
+int attn_prefill_tc2_dispatch(const void* q, const void* k_cache, const void* v_cache, void* out, float* lse, int B, int S,
+                              int past_len, int n_h, int n_kv, int d, int T_max, float scale, cudaStream_t st);
 }
 
 extern "C" {
@@ -386,7 +388,10 @@ int tl_attn_prefill_fwd(const void* q, const void* k_cache, const void* v_cache,
         const char* e = getenv("TL_ATTN_IMPL");          // read per call: tests flip it
         const int impl = !e ? 0 : (e[0] == 'm' ? 1 : (e[0] == 't' ? 2 : 0));
         if (impl == 2 || (impl == 0 && S >= 128)) {
-            const int rc = attn_prefill_tc_dispatch(q, k_cache, v_cache, out, lse, B, S, past_len, n_h, n_kv, d, T_max, scale, st);
+            const char* v = getenv("TL_ATTN_TC");                // 2 (default): O accumulated in TMEM; 1: first form
+            const int rc = (v && v[0] == '1')
+                ? attn_prefill_tc_dispatch(q, k_cache, v_cache, out, lse, B, S, past_len, n_h, n_kv, d, T_max, scale, st)
+                : attn_prefill_tc2_dispatch(q, k_cache, v_cache, out, lse, B, S, past_len, n_h, n_kv, d, T_max, scale, st);
             if (rc != 1) return rc;
         }
     }
