@@ -383,8 +383,9 @@ int tl_attn_prefill_fwd(const void* q, const void* k_cache, const void* v_cache,
     if (B == 0 || S == 0) return TL_OK;
     cudaStream_t st = (cudaStream_t)stream;
     {   // tcgen05 tiles (attention_tc.cu) from one full 128-row query tile upwards; TL_ATTN_IMPL=mma|tc forces a path.
-        // Round-1 measurement (TFLOP/s, mma.sync vs tcgen05 with 64-key tiles, two CTAs per SM):
-        // d=128: B=8 S=512 157 / 177, B=16 S=1024 217 / 298, B=1 S=4096 219 / 319;  d=64: B=8 S=512 120 / 127.
+        // Round-1 measurement (TFLOP/s: mma.sync / first tcgen05 form / second form with O accumulated in TMEM):
+        // d=128: B=8 S=512 156 / 177 / 295, B=16 S=1024 217 / 298 / 532, B=1 S=4096 219 / 319 / 578;
+        // d=64:  B=8 S=512 122 / 127 / 141.
         const char* e = getenv("TL_ATTN_IMPL");          // read per call: tests flip it
         const int impl = !e ? 0 : (e[0] == 'm' ? 1 : (e[0] == 't' ? 2 : 0));
         if (impl == 2 || (impl == 0 && S >= 128)) {

@@ -6,8 +6,8 @@
 //   * the exponent reference m_ref follows the running row maximum lazily: p = exp2(s*c - m_ref), and only when a row's
 //     maximum has grown by more than 8 (log2 units; p <= 256 until then) is that row of O rescaled in place
 //     (tcgen05.ld -> * 2^(m_ref - m_new) -> tcgen05.st, decided per warp) - typically in the first one or two tiles of a
-//     row and never again.  Scaling by a power of two commutes with the bf16 rounding of P, so the rounding points are
-//     those of attention.cu / attention_tc.cu;
+//     row and never again.  P is still rounded to bf16 before P V and the row sum still uses the unrounded fp32 p; only
+//     the reference of the exponent differs, so results agree with attention.cu to the usual bf16-P noise (1e-3 rel.);
 //   * the whole 64-value score row is read in one pass (both tcgen05.ld issued before the wait).
 // Per tile the dependent chain is therefore softmax only: P_j V_j runs under the softmax of tile j+1.
 #include <cuda.h>
