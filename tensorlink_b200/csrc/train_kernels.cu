@@ -64,17 +64,35 @@ __global__ void __launch_bounds__(NB_THREADS) rmsnorm_bwd_kernel(const bf16* __r
         const int idx = threadIdx.x + i * NB_THREADS;
         wreg[i] = idx < nvec ? reinterpret_cast<const uint4*>(w)[idx] : make_uint4(0, 0, 0, 0);
     }
-    for (int row = r0; row < r1; ++row) {
+    // the loads of row r+1 are issued before the two block barriers of row r (the row loop is otherwise one dependent
+    // chain per row: 1.3 TB/s at 4096 x 3584 before this, ncu round 1)
+    uint4 xn[NB_MAXV], dn[NB_MAXV], an[NB_MAXV];
+    auto fetch = [&](int row) {
         const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * H);
         const uint4* dr = reinterpret_cast<const uint4*>(dy + (size_t)row * H);
+        const uint4* ar = dx_add ? reinterpret_cast<const uint4*>(dx_add + (size_t)row * H) : nullptr;
+#pragma unroll
+        for (int i = 0; i < NB_MAXV; ++i) {
+            const int idx = threadIdx.x + i * NB_THREADS;
+            if (idx < nvec) {
+                xn[i] = xr[idx];
+                dn[i] = dr[idx];
+                an[i] = ar ? ar[idx] : make_uint4(0, 0, 0, 0);
+            }
+        }
+    };
+    if (r0 < r1) fetch(r0);
+    for (int row = r0; row < r1; ++row) {
         const float rs = rstd[row];
         float nv[NB_MAXV][8], gv[NB_MAXV][8];
+        uint4 av[NB_MAXV];
         float dot = 0.f;
 #pragma unroll
         for (int i = 0; i < NB_MAXV; ++i) {
             const int idx = threadIdx.x + i * NB_THREADS;
             if (idx < nvec) {
-                const uint4 xv = xr[idx], dv = dr[idx], wv = wreg[i];
+                const uint4 xv = xn[i], dv = dn[i], wv = wreg[i];
+                av[i] = an[i];
                 const uint32_t* x32 = reinterpret_cast<const uint32_t*>(&xv);
                 const uint32_t* d32 = reinterpret_cast<const uint32_t*>(&dv);
                 const uint32_t* w32 = reinterpret_cast<const uint32_t*>(&wv);
@@ -89,6 +107,7 @@ __global__ void __launch_bounds__(NB_THREADS) rmsnorm_bwd_kernel(const bf16* __r
                 }
             }
         }
+        if (row + 1 < r1) fetch(row + 1);
         dot = warp_sum(dot);
         __syncthreads();
         if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
@@ -106,8 +125,7 @@ __global__ void __launch_bounds__(NB_THREADS) rmsnorm_bwd_kernel(const bf16* __r
 #pragma unroll
                 for (int j = 0; j < 8; ++j) o[j] = rbf(rs * (gv[i][j] - nv[i][j] * mean));
                 if (dx_add) {
-                    const uint4 av = reinterpret_cast<const uint4*>(dx_add + (size_t)row * H)[idx];
-                    const uint32_t* a32 = reinterpret_cast<const uint32_t*>(&av);
+                    const uint32_t* a32 = reinterpret_cast<const uint32_t*>(&av[i]);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) { o[2 * j] += bf16_lo(a32[j]); o[2 * j + 1] += bf16_hi(a32[j]); }
                 }
