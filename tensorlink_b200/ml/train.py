@@ -86,9 +86,9 @@ class StageTrainer:
             s["rstd2"] = torch.empty(N, dtype=torch.float32, device=dev)
             s["h2"] = nat.rmsnorm_fwd(s["x_mid"], v[f"l{li}.ln2"], cfg.rms_eps, rstd=s["rstd2"])
             s["gu"] = nat.gemm(s["h2"], v[f"l{li}.wgu"])
-            act = torch.empty(N, cfg.intermediate, dtype=bf, device=dev)
-            nat.swiglu_fwd(s["gu"], act)
-            x = nat.gemm(act, v[f"l{li}.wd"], residual=s["x_mid"])
+            s["act"] = torch.empty(N, cfg.intermediate, dtype=bf, device=dev)     # kept: the down-proj wgrad needs it
+            nat.swiglu_fwd(s["gu"], s["act"])
+            x = nat.gemm(s["act"], v[f"l{li}.wd"], residual=s["x_mid"])
             saved.append(s)
             self.launches += 10
         self.ctx[mb] = {"layers": saved, "b": b, "S": S}
@@ -129,8 +129,7 @@ class StageTrainer:
         for j in reversed(range(len(self.layer_ids))):
             li, s = self.layer_ids[j], c["layers"][j]
             # ---- MLP
-            act = torch.empty(N, cfg.intermediate, dtype=bf, device=dev)
-            nat.swiglu_fwd(s["gu"], act)                                                 # recompute (not saved)
+            act = s["act"]
             d_act = nat.gemm(dy, v[f"l{li}.wd"], flags=B_MN, N=cfg.intermediate)         # dy·Wd
             nat.gemm(dy, act, out=g[f"l{li}.wd"], flags=A_MN | B_MN | ACC, M=H, K=N, N=cfg.intermediate)
             dgu = torch.empty_like(s["gu"])
@@ -159,7 +158,7 @@ class StageTrainer:
             dx = torch.empty(N, H, dtype=bf, device=dev)
             nat.rmsnorm_bwd(s["x_in"], v[f"l{li}.ln1"], dh1, s["rstd1"], dx, self.norm_acc[f"l{li}.ln1"], dx_add=d_xmid)
             dy = dx
-            self.launches += 18
+            self.launches += 17
         return dy.view(b, S, H)
 
     def embed_backward(self, ids: torch.Tensor, dx: torch.Tensor):
