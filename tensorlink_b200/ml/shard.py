@@ -128,6 +128,8 @@ class ShardParams:
     def hf_state_dict(self, grads: bool = False) -> Dict[str, torch.Tensor]:
         """Inverse mapping (the role of ``parameters(distributed=True)``, module.py:577-650)."""
         cfg = self.cfg
+        if grads and getattr(self, "grad_settle", None) is not None:
+            self.grad_settle()          # matrix gradients are zeroed lazily after zero_grad() (ml/train.py)
         src = self.g if grads else self.v
         out: Dict[str, torch.Tensor] = {}
         for li in self.layer_ids:

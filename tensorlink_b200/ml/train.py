@@ -63,6 +63,7 @@ class StageTrainer:
             self._lazy.append("head")
         self._fresh: set = set()
         self._eager = [t for n, t in self.p.g.items() if n not in set(self._lazy)]
+        self.p.grad_settle = self.settle_grads          # gradient export (hf_state_dict(grads=True)) settles first
 
     # ------------------------------------------------------------------------------------------ forward
     def forward_layers(self, mb: int, x: torch.Tensor) -> torch.Tensor:
