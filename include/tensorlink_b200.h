@@ -185,9 +185,9 @@ int tl_peer_free(void* ptr);    /* free a tl_peer_alloc allocation */
 /* ++*want_dev, then wait until *flag_local >= *want_dev (mod 2^32).  After timeout_ns (0 = 10 s) sets *err_dev = 1
  * and returns instead of hanging; once *err_dev is set every later wait returns at once.  wait_ns_dev (optional) accumulates the nanoseconds spent waiting. */
 int tl_peer_wait(const uint32_t* flag_local, uint32_t* want_dev, uint32_t* err_dev, uint64_t* wait_ns_dev,
-                 uint64_t timeout_ns, void* stream);
+                 uint64_t timeout_ns, int32_t* bump_dev, void* stream);   /* bump_dev (optional): ++*bump_dev as well */
 /* ++*sent_dev, then publish it in the peer's flag after every earlier write of this stream (release, system scope) */
-int tl_peer_signal(uint32_t* flag_peer, uint32_t* sent_dev, void* stream);
+int tl_peer_signal(uint32_t* flag_peer, uint32_t* sent_dev, int32_t* bump_dev, void* stream);   /* bump_dev as above */
 /* copy `bytes` (multiple of 16, both 16-byte aligned) into the peer buffer, then signal as above */
 int tl_peer_put(void* dst_peer, const void* src, size_t bytes, uint32_t* flag_peer, uint32_t* sent_dev, void* stream);
 

@@ -29,10 +29,11 @@ __device__ __forceinline__ uint64_t global_ns() {
 
 // ++*want; spin until *flag >= *want.  wait_ns (optional) accumulates the time spent spinning.
 __global__ void peer_wait_kernel(const uint32_t* __restrict__ flag, uint32_t* __restrict__ want, uint32_t* __restrict__ err,
-                                 unsigned long long* __restrict__ wait_ns, uint64_t timeout_ns) {
+                                 unsigned long long* __restrict__ wait_ns, uint64_t timeout_ns, int32_t* __restrict__ bump) {
     if (threadIdx.x != 0) return;
     const uint32_t w = *want + 1u;
     *want = w;
+    if (bump) *bump += 1;             // e.g. the KV length of the step this wait opens (saves a launch per step)
     if (*err) return;                 // an earlier wait already gave up: do not stall the rest of the queue
     const uint64_t t0 = global_ns();
     uint64_t t = t0;
@@ -49,10 +50,11 @@ __global__ void peer_wait_kernel(const uint32_t* __restrict__ flag, uint32_t* __
 }
 
 // ++*sent; publish it in the peer's flag after everything this stream wrote before
-__global__ void peer_signal_kernel(uint32_t* __restrict__ flag_peer, uint32_t* __restrict__ sent) {
+__global__ void peer_signal_kernel(uint32_t* __restrict__ flag_peer, uint32_t* __restrict__ sent, int32_t* __restrict__ bump) {
     if (threadIdx.x != 0) return;
     const uint32_t s = *sent + 1u;
     *sent = s;
+    if (bump) *bump += 1;             // e.g. the cache write position, advanced once the step's kernels are done
     __threadfence_system();
     st_release_sys(flag_peer, s);
 }
@@ -114,16 +116,16 @@ int tl_peer_free(void* ptr) {
 }
 
 int tl_peer_wait(const uint32_t* flag_local, uint32_t* want_dev, uint32_t* err_dev, uint64_t* wait_ns_dev, uint64_t timeout_ns,
-                 void* stream) {
+                 int32_t* bump_dev, void* stream) {
     TL_REQUIRE(flag_local && want_dev && err_dev, TL_ERR_INVALID, "tl_peer_wait: null pointer");
     peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flag_local, want_dev, err_dev, (unsigned long long*)wait_ns_dev,
-                                                         timeout_ns ? timeout_ns : 10000000000ull);
+                                                         timeout_ns ? timeout_ns : 10000000000ull, bump_dev);
     return check_launch("tl_peer_wait");
 }
 
-int tl_peer_signal(uint32_t* flag_peer, uint32_t* sent_dev, void* stream) {
+int tl_peer_signal(uint32_t* flag_peer, uint32_t* sent_dev, int32_t* bump_dev, void* stream) {
     TL_REQUIRE(flag_peer && sent_dev, TL_ERR_INVALID, "tl_peer_signal: null pointer");
-    peer_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flag_peer, sent_dev);
+    peer_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flag_peer, sent_dev, bump_dev);
     return check_launch("tl_peer_signal");
 }
 

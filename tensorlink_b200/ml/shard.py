@@ -336,22 +336,25 @@ class CudaLayerGroup:
         self.kvlen_dev.fill_(past_len + S)
         return w.x.view(B, S, H)
 
-    def decode_step_inplace(self, x: torch.Tensor, out: Optional[torch.Tensor] = None):
+    def decode_step_inplace(self, x: torch.Tensor, out: Optional[torch.Tensor] = None, advance: bool = True):
         """x [B,H] updated in place through this shard's layers; one new token per row at position ``pos_dev``.
         Graph-capturable: the write position and the KV length live in device memory and are advanced by
         kernels inside the same launch sequence (kv_len += 1 before the layers, pos += 1 after).
         ``out``: where the LAST layer's down projection stores the shard's output rows instead of ``x`` — the next
-        stage's peer-mapped input buffer (p2p/peer.py), so the hop rides on that kernel's own stores."""
+        stage's peer-mapped input buffer (p2p/peer.py), so the hop rides on that kernel's own stores.
+        ``advance=False``: the caller advances ``kvlen_dev`` before and ``pos_dev`` after (the mailbox kernels do)."""
         B = x.shape[0]
         w = self._dbufs(B)
-        nat.advance_pos(self.kvlen_dev, None, 1)
+        if advance:
+            nat.advance_pos(self.kvlen_dev, None, 1)
         for j in range(self.num_layers):
             o = out if j == self.num_layers - 1 else None
             if B <= gemv_max_rows():
                 self._layer_decode(j, x, B, w, o)
             else:
                 self._layer_decode_batched(j, x, B, w, o)
-        nat.advance_pos(self.pos_dev, None, 1)
+        if advance:
+            nat.advance_pos(self.pos_dev, None, 1)
 
     def decode_jobs(self, x: torch.Tensor, B: int) -> list:
         """The layer part of a decode step as ``tl_decode_job`` entries (x [B,H] updated in place)."""

@@ -109,21 +109,22 @@ class CudaStage:
     def _decode_body_ring(self, slot: int, B: int, ring):
         """The decode step of a multi-stage pipeline with the hops on peer memory (p2p/peer.py): wait for this slot's
         input in the local mailbox, run the layers, let the last kernel store into the neighbour's mailbox, signal."""
+        grp = self.slots[slot]
         if self.has_embed:
-            ring.wait_ids(slot)
+            ring.wait_ids(slot, bump=grp.kvlen_dev)              # the opening wait also counts the new key in
             ring.log_token(slot, B)
             x = self.x_dec[slot][:B]
             nat.embed_fwd(ring.ids_in[slot][:B], self.params.v["embed"], out=x)
         else:
-            ring.wait_x(slot)
+            ring.wait_x(slot, bump=grp.kvlen_dev)
             x = ring.x_in[slot][:B]
         if self.has_head:
-            self.slots[slot].decode_step_inplace(x)
+            grp.decode_step_inplace(x, advance=False)
             self.head_argmax(x, ring.first_ids_in[slot][:B])
-            ring.signal_ids(slot)
+            ring.signal_ids(slot, bump=grp.pos_dev)              # the closing signal also advances the cache position
         else:
-            self.slots[slot].decode_step_inplace(x, out=ring.next_x_in[slot][:B])
-            ring.signal_x(slot)
+            grp.decode_step_inplace(x, out=ring.next_x_in[slot][:B], advance=False)
+            ring.signal_x(slot, bump=grp.pos_dev)
 
     def _decode_body(self, slot: int, B: int, ring=None):
         if ring is not None:
@@ -175,7 +176,7 @@ class CudaStage:
         # GEMV path: 4 Linears + attention (1 fused / 3); batched: 4 GEMMs + 3 split-K reduce(+norm) passes + attention
         n = len(self.slots[0].layer_ids) * ((7 if gemv else 10) - (2 if fused else 0)) + 2 + (0 if gemv else 1)
         if ring:
-            n += 3 if self.has_embed else 2          # wait (+ token log) + signal
+            n += (3 if self.has_embed else 2) - 2    # wait (+ token log) + signal, which also do the two position updates
         if self.has_embed:
             n += 1
         if self.has_head:

@@ -54,8 +54,8 @@ _SIGS = {
     "tl_peer_open": (c_int, [c_void_p, POINTER(c_void_p)]),
     "tl_peer_close": (c_int, [c_void_p]),
     "tl_peer_free": (c_int, [c_void_p]),
-    "tl_peer_wait": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_uint64, c_void_p]),
-    "tl_peer_signal": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "tl_peer_wait": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_uint64, c_void_p, c_void_p]),
+    "tl_peer_signal": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "tl_peer_put": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "tl_lmhead_ws": (c_size_t, [c_int, c_int]),
     "tl_lmhead_argmax": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_size_t,
@@ -373,14 +373,14 @@ def peer_free(ptr: int):
     _check(load().tl_peer_free(ptr), "tl_peer_free")
 
 
-def peer_wait(flag, want, err, wait_ns=None, timeout_ns: int = 0):
+def peer_wait(flag, want, err, wait_ns=None, timeout_ns: int = 0, bump=None):
     require_device()
-    _check(load().tl_peer_wait(_p(flag), _p(want), _p(err), _p(wait_ns), timeout_ns, _stream()), "tl_peer_wait")
+    _check(load().tl_peer_wait(_p(flag), _p(want), _p(err), _p(wait_ns), timeout_ns, _p(bump), _stream()), "tl_peer_wait")
 
 
-def peer_signal(flag_peer, sent):
+def peer_signal(flag_peer, sent, bump=None):
     require_device()
-    _check(load().tl_peer_signal(_p(flag_peer), _p(sent), _stream()), "tl_peer_signal")
+    _check(load().tl_peer_signal(_p(flag_peer), _p(sent), _p(bump), _stream()), "tl_peer_signal")
 
 
 def peer_put(dst_peer, src, flag_peer, sent):

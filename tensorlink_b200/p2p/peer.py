@@ -84,17 +84,19 @@ class PeerRing:
         self.link.barrier()
 
     # ---- graph-capturable pieces (slot s)
-    def wait_x(self, s: int):
-        nat.peer_wait(self.flag_x[s:s + 1], self.want_x[s:s + 1], self.err, self.wait_ns)
+    # ``bump``: a device int32 the same one-thread kernel increments (the stage's KV length on the opening wait, its
+    # cache position on the closing signal), so a decode step needs no separate bookkeeping launches
+    def wait_x(self, s: int, bump=None):
+        nat.peer_wait(self.flag_x[s:s + 1], self.want_x[s:s + 1], self.err, self.wait_ns, bump=bump)
 
-    def wait_ids(self, s: int):
-        nat.peer_wait(self.flag_ids[s:s + 1], self.want_ids[s:s + 1], self.err, self.wait_ns)
+    def wait_ids(self, s: int, bump=None):
+        nat.peer_wait(self.flag_ids[s:s + 1], self.want_ids[s:s + 1], self.err, self.wait_ns, bump=bump)
 
-    def signal_x(self, s: int):
-        nat.peer_signal(self.next_flag_x[s:s + 1], self.sent_x[s:s + 1])
+    def signal_x(self, s: int, bump=None):
+        nat.peer_signal(self.next_flag_x[s:s + 1], self.sent_x[s:s + 1], bump=bump)
 
-    def signal_ids(self, s: int):
-        nat.peer_signal(self.first_flag_ids[s:s + 1], self.sent_ids[s:s + 1])
+    def signal_ids(self, s: int, bump=None):
+        nat.peer_signal(self.first_flag_ids[s:s + 1], self.sent_ids[s:s + 1], bump=bump)
 
     def log_token(self, s: int, B: int):
         """out_log[s, :B, step] = ids_in[s, :B]; ++step (first stage)."""

@@ -390,10 +390,11 @@ def test_peer_wait_signal_put(nat):
     # a waiter is already spinning (the pipeline loads them when it instantiates its graphs, before any traffic)
     nat.peer_put(buf, rnd(1024, seed=69).cuda(), flag, sent)
     nat.peer_wait(flag, want, err, wait_ns)
-    nat.peer_signal(flag, sent)
-    nat.peer_wait(flag, want, err, wait_ns)
+    bump = torch.zeros(2, dtype=torch.int32, device="cuda")
+    nat.peer_signal(flag, sent, bump=bump[0:1])             # the optional bookkeeping counters advance with the handshake
+    nat.peer_wait(flag, want, err, wait_ns, bump=bump[1:2])
     torch.cuda.synchronize()
-    assert int(want) == 2 and int(sent) == 2 and int(flag) == 2 and int(err) == 0
+    assert int(want) == 2 and int(sent) == 2 and int(flag) == 2 and int(err) == 0 and bump.tolist() == [1, 1]
     wait_ns.zero_()
     s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
     for rnd_i in range(3):
