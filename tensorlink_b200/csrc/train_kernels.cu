@@ -518,7 +518,13 @@ int tl_rmsnorm_bwd(const void* x, const void* w, const void* dy, const float* rs
     using namespace tl;
     TL_REQUIRE(H % 8 == 0 && H <= NB_THREADS * 8 * 8, TL_ERR_INVALID, "tl_rmsnorm_bwd: unsupported H=%d", H);
     if (rows == 0) return TL_OK;
-    int rpb = (rows + sm_count() * 2 - 1) / (sm_count() * 2);
+    static int mult = 0;                       // CTAs per SM worth of row blocks (TL_NB_GRID_MULT, default 2)
+    if (mult == 0) {
+        const char* e = getenv("TL_NB_GRID_MULT");
+        mult = e ? atoi(e) : 2;
+        if (mult < 1 || mult > 16) mult = 2;
+    }
+    int rpb = (rows + sm_count() * mult - 1) / (sm_count() * mult);
     if (rpb < 1) rpb = 1;
     const int grid = (rows + rpb - 1) / rpb;
     const int nv = ((H >> 3) + NB_THREADS - 1) / NB_THREADS;
