@@ -7,6 +7,7 @@ against the reference's worker (its network process, or tests that drive a worke
     _handle_forward(module_id, key, *payload)      :297-357
     _handle_backward(module_id, tag, grad)         :233-295
     _handle_generate(module_id, *payload, stream)  :359-441
+    handle_forward_frame(module_id, key, bytes)    the same forward in the reference's wire format (p2p/wire.py)
     process_state_update(module_id, (op, arg))     :1268-1347
 
 What differs: payloads are device tensors / dicts handed in and returned directly (the reference pulls pickled bytes
@@ -74,6 +75,19 @@ class DistributedWorker:
         else:
             out["hidden_states"] = st.prefill(hs, int(kwargs.get("past_len", 0) or 0), 0).clone()
         return out
+
+    def handle_forward_frame(self, module_id: str, key: Tuple[int, int, str], data: bytes) -> bytes:
+        """The same call in the reference's WIRE format: ``data`` is what the reference user side
+        puts in shared memory for ``send_forward`` (ml/module.py:1549-1556: 8-byte length, args frame, kwargs frame);
+        the return value is the frame its ``check_forward`` poll reads back (ml/worker.py:344-346).  A reference peer's
+        node process can hand the bytes over unchanged; everything between the two frames runs on the device."""
+        from ..p2p import wire
+        _args, kwargs = wire.unpack_forward(data, device=self.device)
+        if "hidden_states" not in kwargs:
+            raise KeyError("forward request carries no hidden_states (a layer-group shard consumes kwargs only, "
+                           "ml/worker.py:332-335)")
+        out = self._handle_forward(module_id, key, kwargs)
+        return wire.encode({k: (v.detach() if isinstance(v, torch.Tensor) else v) for k, v in out.items()})
 
     def _handle_backward(self, module_id: str, tag: Tuple[int, int, str], loss_relay: torch.Tensor) -> torch.Tensor:
         """worker.py:233-295: backward through the shard for the micro-batch ``tag``; returns d(loss)/d(shard input)."""

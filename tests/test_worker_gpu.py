@@ -58,3 +58,27 @@ def test_worker_training_ops():
     assert float((w.modules[mid].params.flat.float() - before.float()).abs().sum()) > 0
     with pytest.raises(KeyError):
         w._handle_backward(mid, key, torch.randn_like(y))                      # intermediates are consumed once
+
+
+def test_forward_in_the_reference_wire_format():
+    """A forward request framed exactly as the reference user side frames it (8-byte length, args frame, kwargs frame with
+    the loop live-ins) goes through ``handle_forward_frame`` and comes back as one frame whose hidden_states equal the
+    direct call, with the other live-ins echoed like ``LayerGroupModule`` does."""
+    from oracle import wire_oracle as W          # the reference-side encoder / decoder (test infrastructure)
+    from tensorlink_b200.ml.worker import DistributedWorker
+    cfg = C.TINY_QWEN2_D128
+    w = DistributedWorker(max_batch=2, max_seq=64)
+    a = w.load_module({"module_id": "a" * 64, "name": cfg.name, "type": "offloaded_group", "layer_range": (1, 2), "training": False})
+    x = (torch.randn(2, 9, cfg.hidden) * 0.5).bfloat16()
+    live_ins = {"hidden_states": x, "position_ids": torch.arange(9)[None].expand(2, -1).contiguous(), "use_cache": False,
+                "causal_mask": None, "position_embeddings": (torch.zeros(2, 9, 8).bfloat16(), torch.ones(2, 9, 8).bfloat16())}
+    args_frame, kwargs_frame = W.encode(()), W.encode(live_ins)
+    request = len(args_frame).to_bytes(8, "big") + args_frame + kwargs_frame
+    reply = W.decode(w.handle_forward_frame(a, (0, 0, a), request))
+    direct = w._handle_forward(a, (0, 1, a), {"hidden_states": x.cuda()})
+    assert set(reply) == set(live_ins)
+    assert reply["hidden_states"].dtype == torch.bfloat16 and torch.equal(reply["hidden_states"], direct["hidden_states"].cpu())
+    assert torch.equal(reply["position_ids"], live_ins["position_ids"]) and reply["use_cache"] is False
+    assert isinstance(reply["position_embeddings"], tuple) and torch.equal(reply["position_embeddings"][1], live_ins["position_embeddings"][1])
+    with pytest.raises(KeyError):
+        w.handle_forward_frame(a, (0, 2, a), (len(args_frame)).to_bytes(8, "big") + args_frame + W.encode({"use_cache": True}))
