@@ -89,6 +89,18 @@ class DistributedWorker:
         out = self._handle_forward(module_id, key, kwargs)
         return wire.encode({k: (v.detach() if isinstance(v, torch.Tensor) else v) for k, v in out.items()})
 
+    def handle_backward_frame(self, module_id: str, tag: Tuple[int, int, str], data: bytes) -> bytes:
+        """Backward in the reference's wire format: ``data`` = one frame holding the gradient of this shard's output
+        (ml/module.py:482-488 -> ml/worker.py:243-246); returns one frame holding the gradient of its input
+        (ml/worker.py:289-291)."""
+        from ..p2p import wire
+        grad = wire.decode(data, device=self.device)
+        if isinstance(grad, (tuple, list)):
+            grad = grad[0]
+        if not isinstance(grad, torch.Tensor):
+            raise TypeError("backward request does not hold a gradient tensor")
+        return wire.encode(self._handle_backward(module_id, tuple(tag), grad.to(torch.bfloat16)))
+
     def _handle_backward(self, module_id: str, tag: Tuple[int, int, str], loss_relay: torch.Tensor) -> torch.Tensor:
         """worker.py:233-295: backward through the shard for the micro-batch ``tag``; returns d(loss)/d(shard input)."""
         st = self.modules[module_id]

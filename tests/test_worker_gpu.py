@@ -58,6 +58,15 @@ def test_worker_training_ops():
     assert float((w.modules[mid].params.flat.float() - before.float()).abs().sum()) > 0
     with pytest.raises(KeyError):
         w._handle_backward(mid, key, torch.randn_like(y))                      # intermediates are consumed once
+    # the same backward framed as the reference frames it: identical input gradient
+    from oracle import wire_oracle as W
+    g = (torch.randn(2, 16, cfg.hidden) * 0.01).bfloat16()
+    k1, k2 = (1, 0, mid), (1, 1, mid)
+    w._handle_forward(mid, k1, {"hidden_states": x})
+    w._handle_forward(mid, k2, {"hidden_states": x})
+    direct = w._handle_backward(mid, k1, g.cuda())
+    framed = W.decode(w.handle_backward_frame(mid, list(k2), W.encode(g)))
+    assert framed.dtype == torch.bfloat16 and torch.equal(framed, direct.cpu())
 
 
 def test_forward_in_the_reference_wire_format():
