@@ -50,6 +50,11 @@ def main(out_dir):
     gen2 = dm2.generate(ids4 if rank == 0 else None, max_new_tokens=5)
     ref_gen = O.OracleModel(cfg, sd, "sdpa_math").generate(ids, 6)
     ref_gen2 = O.OracleModel(cfg, sd, "sdpa_math").generate(ids4, 5)
+    # HF stopping semantics through the pipeline: every rank returns the same trimmed / padded result
+    from tensorlink_b200.ml.module import apply_eos
+    eos = int(ref_gen2[1, 9 + 2])
+    gen_eos = dm2.generate(ids4 if rank == 0 else None, max_new_tokens=5, eos_token_id=eos, pad_token_id=0)
+    res["eos_ok"] = bool(torch.equal(gen_eos, apply_eos(ref_gen2, 9, eos, 0)) and gen_eos.shape[1] <= ref_gen2.shape[1])
     res["gen_equal"] = bool(torch.equal(gen, ref_gen))          # every rank holds the result
     res["gen2_equal"] = bool(torch.equal(gen2, ref_gen2))
     if rank == 0:

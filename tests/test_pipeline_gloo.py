@@ -26,7 +26,7 @@ def test_two_rank_pipeline(tmp_path):
     r0, r1 = torch.load(tmp_path / "rank0.pt"), torch.load(tmp_path / "rank1.pt")
     assert r0["logits_equal"]
     assert r0["gen_equal"] and r1["gen_equal"] and r0["gen2_equal"] and r1["gen2_equal"]
-    assert r0["stream_ok"]
+    assert r0["stream_ok"] and r0["eos_ok"] and r1["eos_ok"]
     assert r0["loss_close"] and r1["loss_close"]
     # bf16 autograd in two halves (grad crossing the rank boundary rounded to bf16 once more) vs one graph
     assert r0["grad_worst_rel_l2"] < 2e-2 and r1["grad_worst_rel_l2"] < 2e-2
