@@ -225,6 +225,10 @@ int tl_colsum(const void* dy, float* db_accum, int M, int N, int ld, void* strea
 int tl_f32_to_bf16_accum(const float* src, void* dst, size_t n, int accumulate, void* stream);
 /* a[n] += b[n] over bf16 (n %% 8 == 0) */
 int tl_add_inplace(void* a, const void* b, size_t n, void* stream);
+/* a[n] = (accumulate ? a[n] : 0) + scale * b[n]: commits a pending gradient with the upstream gradient's scale
+ * (the reference gets this from autograd: ml/worker.py:271 `assoc_output.backward(loss)`); bf16 (n %% 8 == 0) / fp32 */
+int tl_scale_add_bf16(void* a, const void* b, float scale, int accumulate, size_t n, void* stream);
+int tl_scale_add_f32(float* a, const float* b, float scale, int accumulate, size_t n, void* stream);
 /* fused Adam / AdamW (torch.optim update rule, fp32 math and moments) over a flat bf16 parameter arena
  * (all four arrays 16-byte aligned; n arbitrary) */
 int tl_adamw_step(void* param, const void* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,

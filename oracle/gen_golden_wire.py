@@ -12,6 +12,23 @@ from oracle.ref_shim import import_reference
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "ref_wire_frames.pt")
 
 
+class DynamicCache:
+    """Stand-in with the transformers-4.x attribute names the reference codec reads (utils.py:600-603); the installed
+    transformers 5.x class no longer has them.  Only the class NAME and these two lists matter."""
+
+    def __init__(self, key_cache, value_cache):
+        self.key_cache, self.value_cache = key_cache, value_cache
+
+
+def cached_decode_payload():
+    """What a reference user ships for one cached decode step of a 2-layer shard at position 7 (injector.py:508-556)."""
+    g = torch.Generator().manual_seed(78)
+    ks = [torch.randn(1, 2, 7, 16, generator=g).bfloat16() for _ in range(2)]
+    vs = [torch.randn(1, 2, 7, 16, generator=g).bfloat16() for _ in range(2)]
+    return {"hidden_states": torch.randn(1, 1, 64, generator=g).bfloat16(), "cache_position": torch.tensor([7]),
+            "position_ids": torch.tensor([[7]]), "use_cache": True, "past_key_values": DynamicCache(ks, vs)}
+
+
 def payloads():
     g = torch.Generator().manual_seed(77)
     hs = torch.randn(2, 5, 64, generator=g).bfloat16()
@@ -35,7 +52,11 @@ def main():
         back = utils.bytes_to_tensor(f)
         assert type(back) is type(items[k]) or items[k] is None
     items["dropped_object"]["drop"] = None            # what survives the reference codec (utils.py:607)
-    torch.save({"payloads": items, "frames": frames}, OUT)
+    cd = cached_decode_payload()
+    frames_cache = utils.tensor_to_bytes(cd)
+    pkv = cd["past_key_values"]                       # stored as plain lists; the tests rebuild the stand-in object
+    cd["past_key_values"] = {"__dynamic_cache__": True, "key_cache": pkv.key_cache, "value_cache": pkv.value_cache}
+    torch.save({"payloads": items, "frames": frames, "cached_decode": {"payload": cd, "frame": frames_cache}}, OUT)
     print("wrote", OUT, {k: len(v) for k, v in frames.items()})
 
 

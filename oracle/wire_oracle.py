@@ -14,6 +14,9 @@ The skeleton is the payload with every tensor replaced by ``{"__tensor_ref__": "
 anything else ``null``; the blob is ``safetensors.torch.save`` of ``{"__tensor_<i>__": tensor.cpu().contiguous()}``.
 safetensors is a third-party dependency of the reference (pinned 0.4.5 in its lock file; 0.7.0 is installed here —
 the blob format, an 8-byte header length + JSON header + raw little-endian data, is the same).
+A ``DynamicCache`` becomes ``{"__dynamic_cache__": true, "key_cache": [...], "value_cache": [...]}`` (:599-605; the
+reference reads transformers-4.x attribute names, so the golden frame is produced from a stand-in object carrying them);
+``decode`` here keeps that dict instead of rebuilding an HF cache object.
 
 Pinned by tests/test_wire_oracle.py against frames produced by the reference's own ``tensor_to_bytes``
 (oracle/gen_golden_wire.py -> tests/golden/ref_wire_frames.pt): byte-identical.
@@ -49,6 +52,8 @@ def encode(payload: Any) -> bytes:
             return [skeleton(v) for v in o]
         if isinstance(o, _SCALARS):
             return o
+        if o.__class__.__name__ == "DynamicCache":                           # :599-605 (transformers 4.x attribute names)
+            return {"__dynamic_cache__": True, "key_cache": skeleton(o.key_cache), "value_cache": skeleton(o.value_cache)}
         return None                                                          # unserialisable objects are dropped (:607)
 
     head = json.dumps(skeleton(payload)).encode("utf-8")

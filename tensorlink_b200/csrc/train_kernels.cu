@@ -434,6 +434,26 @@ __global__ void add_inplace_kernel(uint4* __restrict__ a, const uint4* __restric
     }
 }
 
+// a[i] = (accumulate ? a[i] : 0) + scale * b[i]  over bf16 (fp32 math, one rounding): commits a pending gradient
+// (produced during the forward pass) into the gradient arena with the upstream gradient's scale
+__global__ void scale_add_bf16_kernel(uint4* __restrict__ a, const uint4* __restrict__ b, float scale, int accumulate, size_t n_vec) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * blockDim.x) {
+        uint4 x = accumulate ? a[i] : make_uint4(0u, 0u, 0u, 0u);
+        const uint4 y = b[i];
+        uint32_t* x32 = reinterpret_cast<uint32_t*>(&x);
+        const uint32_t* y32 = reinterpret_cast<const uint32_t*>(&y);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            x32[j] = pack_bf16(fmaf(scale, bf16_lo(y32[j]), bf16_lo(x32[j])), fmaf(scale, bf16_hi(y32[j]), bf16_hi(x32[j])));
+        a[i] = x;
+    }
+}
+
+__global__ void scale_add_f32_kernel(float* __restrict__ a, const float* __restrict__ b, float scale, int accumulate, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        a[i] = fmaf(scale, b[i], accumulate ? a[i] : 0.f);
+}
+
 // ------------------------------------------------------------------------------------------------ AdamW
 // torch.optim.Adam/AdamW update rule in fp32 on bf16 parameters, fp32 moments
 __device__ __forceinline__ void adamw_one(float& pw, float gr, float& mi, float& vi, float lr, float b1, float b2, float eps,
@@ -622,6 +642,22 @@ int tl_add_inplace(void* a, const void* b, size_t n, void* stream) {
     if (!n) return TL_OK;
     add_inplace_kernel<<<ew_grid(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((uint4*)a, (const uint4*)b, n / 8);
     return check_launch("tl_add_inplace");
+}
+
+int tl_scale_add_bf16(void* a, const void* b, float scale, int accumulate, size_t n, void* stream) {
+    using namespace tl;
+    TL_REQUIRE(n % 8 == 0, TL_ERR_INVALID, "tl_scale_add_bf16: n %% 8 != 0");
+    TL_REQUIRE(((((uintptr_t)a) | ((uintptr_t)b)) & 15) == 0, TL_ERR_INVALID, "tl_scale_add_bf16: 16-byte alignment required");
+    if (!n) return TL_OK;
+    scale_add_bf16_kernel<<<ew_grid(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((uint4*)a, (const uint4*)b, scale, accumulate, n / 8);
+    return check_launch("tl_scale_add_bf16");
+}
+
+int tl_scale_add_f32(float* a, const float* b, float scale, int accumulate, size_t n, void* stream) {
+    using namespace tl;
+    if (!n) return TL_OK;
+    scale_add_f32_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, scale, accumulate, n);
+    return check_launch("tl_scale_add_f32");
 }
 
 int tl_adamw_step(void* param, const void* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,

@@ -62,9 +62,40 @@ def make_plan(cfg: ShardModelConfig, n_stages: int, training: bool = False, bala
     return plan
 
 
+def worker_ranks(plan: Dict[str, dict]) -> Dict[object, int]:
+    """Worker id -> pipeline rank.  Our own plans name ranks directly (ints).  The reference's planner names workers
+    by their node-id hash strings (graphing.py:730-761 `_try_assign_worker` appends the worker's id); those are
+    mapped to ranks in pipeline order = the order in which they first appear walking the plan by layer position."""
+    ids = []
+    for key, e in sorted(plan.items(), key=lambda kv: _plan_position(kv[0], kv[1])):
+        for w in e.get("assigned_workers", []):
+            if w not in ids:
+                ids.append(w)
+    if all(isinstance(w, int) or (isinstance(w, str) and w.isdigit()) for w in ids):
+        return {w: int(w) for w in ids}
+    return {w: i for i, w in enumerate(ids)}
+
+
+def _plan_position(key: str, e: dict):
+    """Sort key that walks a plan front to back: embedding, decoder layers by index, final norm, lm_head."""
+    if "layer_range" in e:
+        return (1, e["layer_range"][0])
+    if ".layers." in key and key.rsplit(".", 1)[1].isdigit():
+        return (1, int(key.rsplit(".", 1)[1]))
+    if "embed" in key:
+        return (0, 0)
+    if key.endswith("lm_head") or key == "lm_head":
+        return (3, 0)
+    if key.endswith("norm"):
+        return (2, 0)
+    return (1, 1 << 30)
+
+
 def stage_layers(plan: Dict[str, dict], rank: int) -> List[int]:
     """Layer ids assigned to ``rank`` by a plan in the reference schema."""
     out: List[int] = []
+    wr = worker_ranks(plan)
+    _ranks = lambda e: [wr[w] for w in e.get("assigned_workers", [])]   # noqa: E731
     for key, e in plan.items():
         if e.get("type") == "offloaded_group" and rank in _ranks(e):
             a, b = e["layer_range"]
@@ -74,9 +105,5 @@ def stage_layers(plan: Dict[str, dict], rank: int) -> List[int]:
     return sorted(out)
 
 
-def _ranks(entry: dict) -> Sequence[int]:
-    return [int(w) if not isinstance(w, int) else w for w in entry.get("assigned_workers", [])]
-
-
 def n_stages(plan: Dict[str, dict]) -> int:
-    return 1 + max(max(_ranks(e), default=0) for e in plan.values())
+    return 1 + max(worker_ranks(plan).values(), default=0)

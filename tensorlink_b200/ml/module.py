@@ -54,6 +54,35 @@ def _config_from_hf(model) -> ShardModelConfig:
                             rms_eps=float(c.rms_norm_eps), max_pos=int(c.max_position_embeddings))
 
 
+# HF forward / generate keywords that change nothing here when left at these values (anything else raises instead of
+# being dropped silently: the reference forwards every keyword to HF, module.py:763-769)
+_NEUTRAL_KW = {"use_cache": (True, False, None), "return_dict": (True, None), "output_attentions": (False, None),
+               "output_hidden_states": (False, None), "num_beams": (1, None), "num_return_sequences": (1, None),
+               "repetition_penalty": (1.0, None), "past_key_values": (None,), "position_ids": (None,),
+               "return_dict_in_generate": (False, None), "temperature": (1.0, None), "top_k": (None, 0, 50),
+               "top_p": (1.0, None), "logits_to_keep": (0, None), "min_new_tokens": (0, None)}
+
+
+def _check_unconsumed(kwargs: dict, what: str):
+    for k, v in kwargs.items():
+        ok = _NEUTRAL_KW.get(k)
+        if ok is None or not any(v is o or (o is not None and v == o) for o in ok):
+            raise NotImplementedError(f"{what}: keyword {k}={v!r} is not supported by the B200 stage executor "
+                                      "(it would be silently ignored otherwise)")
+
+
+def _check_attention_mask(mask, shape):
+    """Only the all-ones mask (no padding) is accepted; a mask with zeros means left/right-padded prompts, whose rows
+    would otherwise attend to pad tokens at shifted positions."""
+    if mask is None:
+        return
+    if tuple(mask.shape) != tuple(shape):
+        raise ValueError(f"attention_mask shape {tuple(mask.shape)} != input_ids shape {tuple(shape)}")
+    if not bool((mask != 0).all()):
+        raise NotImplementedError("padded prompts (attention_mask with zeros) are not supported: pass rows of equal "
+                                  "length, or generate ragged rows one micro-batch at a time")
+
+
 def apply_eos(result: torch.Tensor, prompt_len: int, eos_token_id=None, pad_token_id=None) -> torch.Tensor:
     """HF ``generate`` stopping semantics applied to a finished greedy generation [B, S+new]: everything after a row's
     first EOS becomes ``pad_token_id`` (default: the EOS id) and the result ends where the last row finished.
@@ -192,6 +221,11 @@ class DistributedModel(torch.nn.Module):
         input_ids = kwargs.pop("input_ids", args[0] if args else None)
         labels = kwargs.pop("labels", None)
         gather = kwargs.pop("gather_logits", False)
+        if self.link.first and input_ids is not None:
+            _check_attention_mask(kwargs.pop("attention_mask", None), input_ids.shape)
+        else:
+            kwargs.pop("attention_mask", None)
+        _check_unconsumed(kwargs, "DistributedModel.forward")
         if self.training and getattr(self.stage, "supports_training", False):
             from .train import train_forward
             return train_forward(self, input_ids, labels)
@@ -295,6 +329,11 @@ class DistributedModel(torch.nn.Module):
         if kwargs.pop("do_sample", False):
             raise NotImplementedError("sampling is not implemented; generate() is greedy (do_sample=False)")
         self._eos = (kwargs.pop("eos_token_id", None), kwargs.pop("pad_token_id", None))
+        if self.link.first and input_ids is not None:
+            _check_attention_mask(kwargs.pop("attention_mask", None), input_ids.shape)
+        else:
+            kwargs.pop("attention_mask", None)
+        _check_unconsumed(kwargs, "DistributedModel.generate")
         link, st, cfg = self.link, self.stage, self.cfg
         shape = link.broadcast_object(tuple(input_ids.shape) if link.first else None)
         B, S = shape

@@ -66,6 +66,7 @@ class DistributedWorker:
         st = self.modules[module_id]
         hs = kwargs["hidden_states"].to(self.device)
         out = dict(kwargs)
+        past_len = self._past_len_from_live_ins(st, kwargs, hs)
         if st.supports_training:
             from .train import StageTrainer
             if st.trainer is None:
@@ -73,8 +74,61 @@ class DistributedWorker:
             out["hidden_states"] = st.trainer.forward_layers(key, hs)          # intermediates keyed like :337-341
             st.n_batch += 1
         else:
-            out["hidden_states"] = st.prefill(hs, int(kwargs.get("past_len", 0) or 0), 0).clone()
+            out["hidden_states"] = st.prefill(hs, past_len, 0).clone()
         return out
+
+    @staticmethod
+    def _past_len_from_live_ins(st: CudaStage, kwargs: dict, hs: torch.Tensor) -> int:
+        """Where this call's tokens start in the sequence.  A reference peer never sends ``past_len``: it ships the HF
+        loop live-ins (injector.py:508-556) — ``cache_position`` [S], ``position_ids`` [B,S], ``past_key_values`` (the
+        whole cache, utils.py:599-605) and the 4-D mask.  The KV cache of this stage is RESIDENT, so the position is
+        taken from ``cache_position[0]`` / ``position_ids[:,0]`` and checked against what the stage has cached; inputs
+        this executor cannot honour (padding masks, ragged positions, a shipped cache that disagrees with the resident
+        one) raise instead of computing something else."""
+        B, S = hs.shape[0], hs.shape[1]
+        cand = []
+        if kwargs.get("past_len") is not None:
+            cand.append(int(kwargs["past_len"]))
+        cp = kwargs.get("cache_position")
+        if isinstance(cp, torch.Tensor) and cp.numel():
+            cp = cp.reshape(-1).cpu()
+            if cp.numel() != S or not torch.equal(cp, torch.arange(int(cp[0]), int(cp[0]) + S)):
+                raise ValueError("cache_position must be S consecutive positions")
+            cand.append(int(cp[0]))
+        pid = kwargs.get("position_ids")
+        if isinstance(pid, torch.Tensor) and pid.numel():
+            pid = pid.reshape(-1, S).cpu()
+            if not torch.equal(pid, pid[:1].expand_as(pid)) or not torch.equal(pid[0], torch.arange(int(pid[0, 0]), int(pid[0, 0]) + S)):
+                raise NotImplementedError("per-row / non-consecutive position_ids (left-padded batches) are not supported by the "
+                                          "wire bridge; use DistributedModel.generate(attention_mask=...) on the box instead")
+            cand.append(int(pid[0, 0]))
+        if cand and any(c != cand[0] for c in cand):
+            raise ValueError(f"past_len / cache_position / position_ids disagree: {cand}")
+        past_len = cand[0] if cand else 0
+        am = kwargs.get("attention_mask")
+        if isinstance(am, torch.Tensor) and am.numel():
+            a = am.detach().cpu()
+            if a.dim() == 2:
+                trivial = bool((a != 0).all())
+            else:                                    # HF's additive 4-D mask: causal = zeros on and below the diagonal
+                q = a.shape[-2]
+                ref = torch.ones(q, a.shape[-1], dtype=torch.bool).tril(a.shape[-1] - q)
+                trivial = bool(((a == 0) == ref).all())
+            if not trivial:
+                raise NotImplementedError("padding / custom attention masks are not supported by the wire bridge (the stage applies the causal mask itself)")
+        pkv = kwargs.get("past_key_values")
+        shipped = None
+        if isinstance(pkv, dict) and pkv.get("__dynamic_cache__"):
+            ks = pkv.get("key_cache") or []
+            shipped = int(ks[0].shape[-2]) if len(ks) and isinstance(ks[0], torch.Tensor) and ks[0].numel() else 0
+        if shipped is not None and shipped not in (0, past_len):
+            raise ValueError(f"shipped past_key_values hold {shipped} positions but the call starts at {past_len}")
+        if past_len and not st.supports_training:
+            cached = int(st.slots[0].pos_dev.item())
+            if cached != past_len:
+                raise ValueError(f"call starts at position {past_len} but this stage has {cached} positions cached "
+                                 "(the KV cache is resident on the stage; it is not rebuilt from a shipped cache)")
+        return past_len
 
     def handle_forward_frame(self, module_id: str, key: Tuple[int, int, str], data: bytes) -> bytes:
         """The same call in the reference's WIRE format: ``data`` is what the reference user side
@@ -118,6 +172,9 @@ class DistributedWorker:
         if not (st.has_embed and st.has_head):
             raise ValueError("generate needs a module loaded with has_embed=True and has_head=True (entire model)")
         B, S = input_ids.shape
+        if B > st.max_batch or S + max_new_tokens > st.max_seq:
+            raise ValueError(f"module sized for batch<={st.max_batch}, T<={st.max_seq}; got batch {B}, "
+                             f"{S} prompt + {max_new_tokens} new tokens")
         ids = input_ids.to(self.device)
         x = st.prefill(st.embed(ids), 0, 0)
         st.head_argmax(x[:, -1, :].contiguous(), st.ids_dec[0][:B])

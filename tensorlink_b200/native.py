@@ -77,6 +77,8 @@ _SIGS = {
     "tl_colsum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "tl_f32_to_bf16_accum": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "tl_add_inplace": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tl_scale_add_bf16": (c_int, [c_void_p, c_void_p, c_float, c_int, c_size_t, c_void_p]),
+    "tl_scale_add_f32": (c_int, [c_void_p, c_void_p, c_float, c_int, c_size_t, c_void_p]),
     "tl_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float, c_float, c_float,
                               c_float, c_int, c_int, c_void_p]),
 }
@@ -455,6 +457,17 @@ def f32_to_bf16_accum(src, dst, accumulate: bool):
 def add_inplace(a, b):
     require_device(); _bf16(a, b)
     _check(load().tl_add_inplace(_p(a), _p(b), a.numel(), _stream()), "tl_add_inplace")
+
+
+def scale_add(a, b, scale: float, accumulate: bool = True):
+    """a = (a if accumulate else 0) + scale * b   (bf16 or fp32 pairs, same shape)."""
+    require_device()
+    assert a.dtype == b.dtype and a.numel() == b.numel() and a.is_contiguous() and b.is_contiguous()
+    if a.dtype == torch.bfloat16:
+        _check(load().tl_scale_add_bf16(_p(a), _p(b), scale, int(accumulate), a.numel(), _stream()), "tl_scale_add_bf16")
+    else:
+        assert a.dtype == torch.float32
+        _check(load().tl_scale_add_f32(_p(a), _p(b), scale, int(accumulate), a.numel(), _stream()), "tl_scale_add_f32")
 
 
 def adamw_step(param, grad, m, v, lr, beta1, beta2, eps, wd, step: int, decoupled: bool):

@@ -12,6 +12,10 @@ they are and anything else ``null``; the blob holds the tensors under those name
 Forward request (ml/module.py:1549-1556 -> ml/worker.py:301-307): ``[8-byte big-endian len(args frame)][args frame]
 [kwargs frame]``; the reply is one frame holding the shard's output dict (ml/worker.py:344-346).
 
+A ``DynamicCache`` is encoded like the reference does (``{"__dynamic_cache__": true, "key_cache": [...],
+"value_cache": [...]}``, utils.py:599-605); ``decode`` leaves it as that dict (re-encoding it reproduces the same
+bytes), because the stage keeps its KV cache resident and only inspects the shipped one for its length.
+
 On-box hops never use this (they are device-to-device, p2p/link.py, p2p/peer.py); it exists for the boundary to the
 reference's own processes.  tests/test_wire_cpu.py pins `encode` byte-for-byte to frames the reference produced.
 """
@@ -27,6 +31,20 @@ from safetensors.torch import save as _blob_save
 _PLAIN = (int, float, bool, str, type(None))
 
 
+def _is_dynamic_cache(node: Any) -> bool:
+    return node.__class__.__name__ == "DynamicCache"
+
+
+def _cache_lists(cache: Any):
+    """Per-layer key / value tensors of an HF DynamicCache: ``key_cache`` / ``value_cache`` (transformers 4.x, what the
+    reference reads, utils.py:600-603) or ``layers[i].keys`` / ``.values`` (5.x)."""
+    if hasattr(cache, "key_cache"):
+        return list(cache.key_cache), list(cache.value_cache)
+    layers = getattr(cache, "layers", [])
+    return ([getattr(l, "keys", None) for l in layers if getattr(l, "keys", None) is not None],
+            [getattr(l, "values", None) for l in layers if getattr(l, "values", None) is not None])
+
+
 class _Encoder:
     def __init__(self):
         self.tensors: Dict[str, torch.Tensor] = {}
@@ -38,6 +56,11 @@ class _Encoder:
             return {"__tensor_ref__": name, "dtype": str(node.dtype), "shape": list(node.shape)}
         if isinstance(node, dict):
             return {key: self.walk(val) for key, val in node.items()}
+        if _is_dynamic_cache(node):
+            # utils.py:599-605: a DynamicCache travels as its per-layer key / value lists
+            keys, vals = _cache_lists(node)
+            return {"__dynamic_cache__": True, "key_cache": [self.walk(k) for k in keys],
+                    "value_cache": [self.walk(v) for v in vals]}
         if isinstance(node, tuple):
             return {"__tuple__": True, "data": [self.walk(val) for val in node]}
         if isinstance(node, list):

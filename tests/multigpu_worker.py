@@ -86,6 +86,13 @@ def main(out_dir):
                               optimizer=torch.optim.Adam)
         s1(tt, labels=tt).loss.backward()
         torch.save(s1.stage.params.g["embed"].cpu(), os.path.join(out_dir, "tied_ref.pt"))
+    # gradient accumulation on the tied split: a second backward without zero_grad must add ITS delta once on both copies
+    ot2 = dtie(tt if rank == 0 else None, labels=tt if rank == 0 else None)
+    ot2.loss.backward()
+    torch.save(dtie.stage.params.g[key].cpu(), os.path.join(out_dir, f"tied2_{rank}.pt"))
+    if rank == 0:
+        s1(tt, labels=tt).loss.backward()
+        torch.save(s1.stage.params.g["embed"].cpu(), os.path.join(out_dir, "tied2_ref.pt"))
     torch.save(grads, os.path.join(out_dir, f"grads{rank}.pt"))
     torch.save(res, os.path.join(out_dir, f"rank{rank}.pt"))
     dist.barrier()

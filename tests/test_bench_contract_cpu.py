@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_one_contract_line():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "tiny", "--steps", "1",
-                        "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                        "--warmup", "1", "--train-model", "tiny-qwen2-d128", "--train-seq", "64"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, lines
@@ -24,3 +24,6 @@ def test_reference_arm_prints_one_contract_line():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     hop = cb["reference_hop"]
     assert hop["decode"]["seconds"] > 0 and hop["prefill"]["payload_bytes"] > hop["decode"]["payload_bytes"]
+    # the training half of BASELINE's metric travels on the same line
+    tr = d["train"]
+    assert tr["unit"] == "samples/s" and tr["value"] > 0 and tr["cpu_baseline"]["kind"] == "port" and tr["cpu_baseline"]["cores"] >= 1

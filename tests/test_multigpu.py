@@ -39,6 +39,9 @@ def test_two_gpu_pipeline_equals_single_stage(tmp_path):
     t0, t1, tr = torch.load(tmp_path / "tied0.pt"), torch.load(tmp_path / "tied1.pt"), torch.load(tmp_path / "tied_ref.pt")
     assert torch.equal(t0, t1)                                        # both copies of the tied weight see the same gradient
     assert (t0.float() - tr.float()).norm() / tr.float().norm() < 5e-3   # = single-stage sum up to bf16 add order
+    a0, a1, ar = torch.load(tmp_path / "tied2_0.pt"), torch.load(tmp_path / "tied2_1.pt"), torch.load(tmp_path / "tied2_ref.pt")
+    assert torch.equal(a0, a1)                                        # still equal after an accumulated second backward
+    assert (a0.float() - ar.float()).norm() / ar.float().norm() < 5e-3   # = twice the gradient, not 2(E+H)+E+H
 
 
 @pytest.mark.parametrize("world,rows", [(2, 2), (2, 5), (4, 2)])

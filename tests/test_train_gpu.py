@@ -227,3 +227,53 @@ def test_training_loss_decreases():
         losses.append(float(out.loss))
     print("losses", [round(l, 4) for l in losses])
     assert losses[-1] < losses[0] - 0.5
+
+
+def test_upstream_gradient_scales_every_parameter():
+    """``(loss * c).backward()`` (gradient accumulation, loss scaling): EVERY gradient is multiplied by c — including
+    the lm_head and final-norm gradients, which are produced during the forward pass — and a training-mode forward
+    that is never followed by backward leaves the gradient arena untouched (autograd semantics of the reference,
+    ml/worker.py:271)."""
+    from tensorlink_b200.ml import DistributedModel
+    for cfg in (C.TINY_QWEN2_D128, C.TINY_QWEN2):                 # untied and tied lm_head
+        ids = synthetic_tokens(cfg, 2, 24)
+        dm = DistributedModel(cfg, training=True, max_batch=2, max_seq=32, optimizer=torch.optim.Adam)
+        opt = dm.create_optimizer(lr=1e-3)
+        opt.zero_grad()
+        dm(ids, labels=ids).loss.backward()
+        full = {k: v.clone() for k, v in dm.stage.params.hf_state_dict(grads=True).items()}
+        opt.zero_grad()
+        dm(ids, labels=ids)                                        # forward only: nothing may reach the arena
+        untouched = dm.stage.params.hf_state_dict(grads=True)
+        assert all(float(v.float().abs().sum()) == 0.0 for v in untouched.values())
+        (dm(ids, labels=ids).loss * 0.5).backward()
+        half = dm.stage.params.hf_state_dict(grads=True)
+        for k, v in full.items():
+            assert torch.equal(half[k].float() * 2, v.float()), k   # a power of two: exact in bf16
+        # accumulation: a second backward without zero_grad adds the same gradient again
+        (dm(ids, labels=ids).loss * 0.5).backward()
+        acc = dm.stage.params.hf_state_dict(grads=True)
+        for k in ("lm_head.weight", "model.norm.weight", "model.layers.0.mlp.down_proj.weight", "model.embed_tokens.weight"):
+            assert O.rel_l2(acc[k], full[k]) <= 4e-3, k
+
+
+def test_deferred_weight_gradients_equal_per_micro_batch_accumulation():
+    """n micro-batches: one weight-gradient GEMM per weight over all tokens of the step (fp32 accumulation over the
+    whole contraction) vs the single-micro-batch step on the same rows — same loss, gradients within one bf16 rounding."""
+    from tensorlink_b200.ml import DistributedModel
+    cfg = C.TINY_QWEN3
+    ids = synthetic_tokens(cfg, 4, 32)
+    out = {}
+    for n_mb in (1, 4):
+        dm = DistributedModel(cfg, training=True, n_pipelines=n_mb, max_batch=4, max_seq=32, optimizer=torch.optim.Adam)
+        opt = dm.create_optimizer(lr=1e-3)
+        opt.zero_grad()
+        o = dm(ids, labels=ids)
+        o.loss.backward()
+        out[n_mb] = (float(o.loss), dm.stage.params.hf_state_dict(grads=True))
+        assert dm.stage.trainer.defer_w == (n_mb > 1)
+        opt.step()                                                 # layer-wise Adam on the side stream must see final grads
+        torch.cuda.synchronize()
+    assert abs(out[1][0] - out[4][0]) < 2e-3
+    for k, v in out[1][1].items():
+        assert O.rel_l2(out[4][1][k], v) <= 6e-3, k

@@ -49,3 +49,35 @@ def test_truncated_input_is_rejected():
         wire.unpack_forward(bytes(4))
     with pytest.raises(ValueError):
         wire.unpack_forward((10 ** 6).to_bytes(8, "big") + f)
+
+
+class DynamicCache:
+    """Same stand-in as oracle/gen_golden_wire.py: the class name and the 4.x attribute names are what the codec keys on."""
+
+    def __init__(self, key_cache, value_cache):
+        self.key_cache, self.value_cache = key_cache, value_cache
+
+
+def test_dynamic_cache_branch_matches_the_reference_codec():
+    """utils.py:599-605: a cached decode step ships the whole DynamicCache; the frame the reference's own codec produced
+    for it (golden) is reproduced byte for byte by the product codec and by the oracle, from the object form."""
+    g = torch.load(GOLD)["cached_decode"]
+    payload = dict(g["payload"])
+    as_dict = payload["past_key_values"]
+    payload["past_key_values"] = DynamicCache(as_dict["key_cache"], as_dict["value_cache"])
+    assert wire.encode(payload) == g["frame"] == W.encode(payload)
+    back = wire.decode(g["frame"])
+    assert _same(back, g["payload"])                      # decoded form: the dict (re-encodes to the same bytes)
+    assert wire.encode(back) == g["frame"]
+
+
+def test_dynamic_cache_with_transformers5_layout():
+    """transformers 5.x keeps keys/values in ``cache.layers[i].keys/.values``; the product codec reads both layouts."""
+    from transformers import DynamicCache as HFCache
+    g = torch.load(GOLD)["cached_decode"]["payload"]["past_key_values"]
+    c = HFCache()
+    for li, (k, v) in enumerate(zip(g["key_cache"], g["value_cache"])):
+        c.update(k, v, li)
+    frame = wire.encode({"past_key_values": c})
+    back = wire.decode(frame)["past_key_values"]
+    assert back["__dynamic_cache__"] is True and _same(back["key_cache"], g["key_cache"]) and _same(back["value_cache"], g["value_cache"])

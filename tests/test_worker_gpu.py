@@ -91,3 +91,55 @@ def test_forward_in_the_reference_wire_format():
     assert isinstance(reply["position_embeddings"], tuple) and torch.equal(reply["position_embeddings"][1], live_ins["position_embeddings"][1])
     with pytest.raises(KeyError):
         w.handle_forward_frame(a, (0, 2, a), (len(args_frame)).to_bytes(8, "big") + args_frame + W.encode({"use_cache": True}))
+
+
+def test_cached_decode_call_from_a_reference_peer():
+    """What an unmodified reference user ships for a cached decode step (injector.py:508-556): hidden_states [B,1,H],
+    ``cache_position`` / ``position_ids`` naming the position and the whole DynamicCache.  The stage's KV cache is
+    resident: the position comes from the live-ins, is checked against the resident cache, and the step equals the
+    direct cached call; inputs the executor cannot honour raise instead of computing at position 0."""
+    from oracle import wire_oracle as W
+    from tensorlink_b200.ml.worker import DistributedWorker
+    cfg = C.TINY_QWEN2_D128
+    w = DistributedWorker(max_batch=1, max_seq=64)
+    a = w.load_module({"module_id": "a" * 64, "name": cfg.name, "type": "offloaded_group", "layer_range": (0, 1), "training": False})
+    b = w.load_module({"module_id": "b" * 64, "name": cfg.name, "type": "offloaded_group", "layer_range": (0, 1), "training": False})
+    x = (torch.randn(1, 7, cfg.hidden) * 0.5).bfloat16()
+    x1 = (torch.randn(1, 1, cfg.hidden) * 0.5).bfloat16()
+    # module b: the direct cached call (prefill 7, then one token at past_len 7)
+    w._handle_forward(b, (0, 0, b), {"hidden_states": x.cuda()})
+    want = w._handle_forward(b, (1, 0, b), {"hidden_states": x1.cuda(), "past_len": 7})["hidden_states"].cpu()
+    # module a: the same two calls framed like the reference frames them
+    def req(kw):
+        af = W.encode(())
+        return len(af).to_bytes(8, "big") + af + W.encode(kw)
+    w.handle_forward_frame(a, (0, 0, a), req({"hidden_states": x, "cache_position": torch.arange(7), "use_cache": True}))
+
+    class DynamicCache:                         # transformers-4.x attribute names, what the reference codec reads
+        def __init__(self, k, v):
+            self.key_cache, self.value_cache = k, v
+    shipped = DynamicCache([torch.zeros(1, cfg.n_kv_heads, 7, cfg.head_dim).bfloat16()] * 2,
+                           [torch.zeros(1, cfg.n_kv_heads, 7, cfg.head_dim).bfloat16()] * 2)
+    step = {"hidden_states": x1, "cache_position": torch.tensor([7]), "position_ids": torch.tensor([[7]]), "use_cache": True,
+            "past_key_values": shipped}
+    got = W.decode(w.handle_forward_frame(a, (1, 0, a), req(step)))
+    assert torch.equal(got["hidden_states"], want)
+    assert got["past_key_values"]["__dynamic_cache__"] is True            # echoed like LayerGroupModule echoes its kwargs
+    # a call whose position disagrees with the resident cache, or with padding, must not run silently
+    with pytest.raises(ValueError):
+        w.handle_forward_frame(a, (2, 0, a), req({"hidden_states": x1, "cache_position": torch.tensor([3])}))
+    with pytest.raises(NotImplementedError):
+        w.handle_forward_frame(a, (3, 0, a), req({"hidden_states": x, "attention_mask": torch.tensor([[0, 0, 1, 1, 1, 1, 1]])}))
+    with pytest.raises(NotImplementedError):
+        w.handle_forward_frame(a, (4, 0, a), req({"hidden_states": x, "position_ids": torch.tensor([[0, 0, 0, 1, 2, 3, 4]])}))
+
+
+def test_generate_bounds_are_checked():
+    from tensorlink_b200.ml.worker import DistributedWorker
+    cfg = C.TINY_QWEN2
+    w = DistributedWorker(max_batch=1, max_seq=32)
+    full = w.load_module({"module_id": "f" * 64, "name": cfg.name, "type": "offloaded", "has_embed": True, "has_head": True})
+    with pytest.raises(ValueError):
+        w._handle_generate(full, synthetic_tokens(cfg, 1, 30).cuda(), max_new_tokens=8)      # 38 > max_seq: would write past the cache
+    with pytest.raises(ValueError):
+        w._handle_generate(full, synthetic_tokens(cfg, 2, 8).cuda(), max_new_tokens=4)       # 2 rows > max_batch
