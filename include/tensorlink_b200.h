@@ -137,15 +137,19 @@ int tl_advance_pos(int32_t* pos_dev, int32_t* kv_len_dev, int delta, void* strea
  * (replaces the per-token TOKEN packet, tensorlink/p2p/torch_node.py:543-551) */
 int tl_append_token(const int64_t* ids, int64_t* out_tokens, int32_t* step_dev, int B, int ld, void* stream);
 
-/* ---- one decode step of a pipeline stage as ONE persistent kernel (csrc/decode_step.cu) -------------------
+/* ---- a chain of dependent decode-step jobs as ONE persistent kernel (csrc/decode_chain.cu) ----------------
  * The job list replaces the per-layer launch sequence of `DistributedWorker._handle_forward` ->
- * `module(**kwargs)` (tensorlink/ml/worker.py:297-357) for single-token rows: the weight stream of job j+1
- * is prefetched while job j finishes, grid barriers publish each job's output vector. */
+ * `module(**kwargs)` (tensorlink/ml/worker.py:297-357) for single-token rows (M <= 4): one CTA per SM walks the
+ * list; the producer warp streams the weights of EVERY GEMV job through one shared-memory ring without ever waiting
+ * for a dependency, a dependency between jobs is one release/acquire counter, the attention job is split-KV over
+ * all CTAs (one group per row and kv head).  Typical chain = one decoder layer:
+ *   ATTN(j) -> GEMV o(j) -> GEMV gate/up(j) -> GEMV down(j) -> GEMV qkv(j+1). */
 #define TL_JOB_GEMV 0     /* y[M,N or N/2] = f(norm(x)[M,K] W[N,K]^T): same semantics and flags as tl_gemv_bf16 */
-#define TL_JOB_ATTN 1     /* RoPE + KV append + attention: same semantics as tl_attn_decode_fused (x = qkv, y = out) */
-#define TL_JOB_EMBED 2    /* y[m,:] = W[ids[m],:]: x = int64 ids, W = table[N=vocab, K=hidden] */
-#define TL_JOB_ARGMAX 3   /* y = int64 ids[M] = argmax over x = bf16 logits[M,N]; W = workspace (>= M*grid*8 bytes) */
-#define TL_JOB_ADVANCE 4  /* *pos_dev += 1; if y != NULL *(int32*)y = new pos */
+#define TL_JOB_ATTN 1     /* RoPE (+ q/k norm) + KV append + attention for one new token per row: x = qkv[M,(n_h+2n_kv)d]
+                           * (post-bias), y = out[M,n_h*d]; reads the position from *pos_dev (cached keys 0..pos-1) */
+#define TL_ATTN_POS_PER_ROW 1   /* flags of an ATTN job: pos_dev is int32[M], one position per row (ragged batches) */
+#define TL_DECODE_CHAIN_MAX_JOBS 16
+#define TL_DECODE_CHAIN_SYNC_BYTES 1024   /* per launch site, zero-initialised once; the kernel leaves it zeroed */
 typedef struct tl_decode_job {
     int32_t type, N, K, flags;
     int32_t n_h, n_kv, d, T_max;
@@ -164,11 +168,14 @@ typedef struct tl_decode_job {
     void* k_cache;
     void* v_cache;
 } tl_decode_job;
-/* sync_ws: >= tl_decode_step_ws(M) bytes, zero-initialised once (the kernel leaves it zeroed).  jobs_host is the
- * host copy of the same list (shape validation and shared-memory sizing); M <= 4 rows. */
-size_t tl_decode_step_ws(int M);
-int tl_decode_step(const tl_decode_job* jobs_dev, const tl_decode_job* jobs_host, int n_jobs, int M, void* sync_ws,
-                   void* stream);
+/* bytes of the attention-partials workspace shared by every chain launch of a stage */
+size_t tl_decode_chain_ws(int M, int n_h, int n_kv, int d);
+/* jobs: HOST array (copied into kernel parameter space).  sync_slot: TL_DECODE_CHAIN_SYNC_BYTES of device memory
+ * private to this launch site (consecutive launches under programmatic dependent launch must not share one); word 2
+ * is an error flag the kernel raises instead of hanging when a dependency wait exceeds 2 s.  pf_ptr/pf_bytes:
+ * optional L2 prefetch hint = the weights the NEXT launch streams first. */
+int tl_decode_chain(const tl_decode_job* jobs, int n_jobs, int M, void* sync_slot, void* attn_ws, size_t attn_ws_bytes,
+                    const void* pf_ptr, size_t pf_bytes, void* stream);
 
 /* ---- peer-memory mailboxes: the inter-shard hop of a decode step (csrc/peer.cu) ---------------------------
  * Replace the per-hop send of `DistributedModel.forward` (tensorlink/ml/module.py:438-462: tensor -> bytes ->

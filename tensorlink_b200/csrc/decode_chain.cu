@@ -1,0 +1,726 @@
+// A chain of dependent decode-step jobs as ONE persistent kernel: the HBM stream never stops at a dependency.
+//
+// The per-kernel decode path (gemv_stream.cu + attention.cu) pays, at every launch boundary, the tail of one kernel,
+// the ramp-up of the next and (for the attention launch) a few microseconds in which nothing streams at all: the two
+// small Linears of a layer (qkv 33 MB, o 26 MB at Qwen2.5-7B) ran at 2.1 / 1.8 TB/s for that reason (round 1).
+// Here one CTA per SM stays resident for a whole decoder layer (or any job list up to DC_MAX_JOBS) and walks it:
+//
+//     ATTN(j)  ->  GEMV o(j) (+residual)  ->  GEMV gate/up(j) (+norm, SwiGLU)  ->  GEMV down(j) (+residual)
+//              ->  GEMV qkv(j+1) (+norm, bias)
+//
+// * The producer warp streams the weight rows of EVERY GEMV job of the chain, in order, into one shared-memory ring
+//   (cp.async.bulk, mbarrier full/empty) and never waits for a dependency: weights are constant.  While the consumer
+//   warps cross a grid barrier, stage the next input vector or run the attention job, the ring (~160-190 KB per SM,
+//   ~25 MB chip-wide, about 4 us of streaming) fills with the next job's weights.
+// * A dependency is one counter in global memory: writers publish with red.release.gpu, every CTA's thread 0 polls
+//   with ld.acquire.gpu.  No cooperative-groups grid sync, no per-thread fences.  Every spin gives up after 2 s and
+//   raises an error word instead of hanging the GPU.
+// * The attention job is split-KV over ALL CTAs, once per kv head (GQA: the n_rep query heads that share a kv head are
+//   handled together, so every cached key / value byte is read exactly once chip-wide): CTA = (row, kv head, key
+//   range) -> partial (m, l, o) per query head -> the last CTA of a (row, kv head) group to arrive combines the
+//   partials and publishes the group; RoPE, the Qwen3 q/k norm and the KV append are fused in.
+// * Job descriptors travel in kernel parameter space (constant bank): no global-memory fetch at a job boundary.
+// * Programmatic dependent launch on both sides; after its last load the producer queues L2 prefetches of the next
+//   launch's first weights.
+// Arithmetic and rounding points of the GEMV jobs are those of gemv_stream_kernel (bit-identical); the attention
+// job follows the SDPA contract of attn_decode_* (P rounded to bf16 before P.V, fp32 accumulation).
+// Algorithmic bytes per launch = sum over the GEMV jobs of 2*N*K  +  the KV bytes of the attention jobs.
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace tl {
+
+constexpr int DC_CW = 8;                       // consumer warps
+constexpr int DC_CT = DC_CW * 32;              // consumer threads
+constexpr int DC_THREADS = DC_CT + 32;         // + producer warp
+constexpr int DC_STAGE = 16 * 1024;
+constexpr int DC_KC = 4096;
+constexpr int DC_MAX_STAGES = 16;
+constexpr int DC_MAX_JOBS = 16;
+constexpr int DC_MAX_M = 4;
+constexpr int DC_MIN_KEYS = 32;                // an attention CTA takes at least this many keys
+constexpr int DC_ATTN_FIXED = 8 * 128 + 128 + 128 + 8 * 128 + 64 + 16;   // floats: sq, sk, sv, so, sred, sml
+constexpr unsigned long long DC_TIMEOUT_NS = 2000000000ull;
+
+struct ChainParams {
+    int n_jobs, n_stages, NW, xs_bytes;
+    int chunk_cap, pad0;
+    unsigned* sync;                 // [0] barrier counter, [1] exit counter, [2] error word, [4..] group counters
+    float* attn_part;               // [M*n_h][cpg][D+2] partial (o, m, l)
+    const unsigned char* pf_ptr;
+    unsigned long long pf_bytes;
+    tl_decode_job jobs[DC_MAX_JOBS];
+};
+
+__device__ __forceinline__ void dc_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ unsigned dc_ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void dc_red_release(unsigned* p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long dc_timer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ uint4 dc_ldcg_v4(const void* p) {      // L2-coherent load of data written by other CTAs
+    uint4 r;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float dc_ldcg_bf16(const bf16* p) {
+    unsigned short v;
+    asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(v) : "l"(p));
+    return __uint_as_float(((uint32_t)v) << 16);
+}
+// wait on an mbarrier, giving up when the CTA has been declared dead (a grid-level wait timed out)
+__device__ __forceinline__ bool dc_mbar_wait(uint64_t* bar, uint32_t parity, volatile int* dead) {
+    int it = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (((++it) & 0xfff) == 0 && *dead) return false;
+    }
+    return true;
+}
+
+struct DcGeom {
+    int npairs, p_begin, p_end, P, n_units, n_groups, KC, n_chunks;
+    bool chunked;
+};
+__device__ __forceinline__ DcGeom dc_geom(int N, int K, int NW) {
+    DcGeom g;
+    g.npairs = N >> 1;
+    g.p_begin = (int)((long long)blockIdx.x * g.npairs / gridDim.x);
+    g.p_end = (int)((long long)(blockIdx.x + 1) * g.npairs / gridDim.x);
+    g.chunked = K > DC_KC || (size_t)K * 4 > DC_STAGE;
+    g.P = g.chunked ? 1 : min(8, (int)(DC_STAGE / ((size_t)K * 4)));
+    g.n_units = (g.p_end - g.p_begin + g.P - 1) / g.P;
+    g.n_groups = (g.n_units + NW - 1) / NW;
+    g.KC = g.chunked ? DC_KC : K;
+    g.n_chunks = (K + g.KC - 1) / g.KC;
+    return g;
+}
+
+template <int M>
+__global__ void __launch_bounds__(DC_THREADS, 1) decode_chain_kernel(const __grid_constant__ ChainParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int n_stages = p.n_stages, NW = p.NW;
+    unsigned char* ring = smem;
+    bf16* xs = reinterpret_cast<bf16*>(smem + (size_t)n_stages * DC_STAGE);                       // [M][K_max]
+    float* attn_s = reinterpret_cast<float*>(smem + (size_t)n_stages * DC_STAGE + (size_t)p.xs_bytes);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(attn_s + DC_ATTN_FIXED + (size_t)8 * p.chunk_cap);
+    uint64_t* empty_bar = full_bar + DC_MAX_STAGES;
+    __shared__ float s_part[DC_CW][M];
+    __shared__ int s_dead, s_last;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < n_stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        s_dead = 0;
+        s_last = 0;
+        fence_barrier_init();
+    }
+    __syncthreads();
+    // programmatic dependent launch: the next kernel may be scheduled as soon as every CTA of this grid is past this
+    // point (its CTAs become resident as ours exit; its producer then streams while our last CTAs drain)
+    asm volatile("griddepcontrol.launch_dependents;");
+
+    if (warp == DC_CW) {
+        // ================================================================= producer: weights of every GEMV job, in order
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            bool alive = true;
+            for (int j = 0; j < p.n_jobs && alive; ++j) {
+                const tl_decode_job& jb = p.jobs[j];
+                if (jb.type != TL_JOB_GEMV) continue;
+                const DcGeom g = dc_geom(jb.N, jb.K, NW);
+                const bf16* W = reinterpret_cast<const bf16*>(jb.W);
+                const int K = jb.K;
+                for (int gi = 0; gi < g.n_groups && alive; ++gi)
+                    for (int c = 0; c < g.n_chunks && alive; ++c)
+                        for (int w = 0; w < NW; ++w) {
+                            const int unit = gi * NW + w;
+                            if (!dc_mbar_wait(&empty_bar[stage], phase ^ 1, &s_dead)) { alive = false; break; }
+                            unsigned char* dst = ring + (size_t)stage * DC_STAGE;
+                            if (unit >= g.n_units) {
+                                mbar_expect_tx(&full_bar[stage], 0);
+                            } else {
+                                const int pair0 = g.p_begin + unit * g.P;
+                                const int np = min(g.P, g.p_end - pair0);
+                                if (!g.chunked) {
+                                    const uint32_t bytes = (uint32_t)(2 * np) * (uint32_t)K * 2u;
+                                    mbar_expect_tx(&full_bar[stage], bytes);
+                                    bulk_load_1d(dst, W + (size_t)(2 * pair0) * K, bytes, &full_bar[stage]);
+                                } else {
+                                    const int k0 = c * g.KC;
+                                    const uint32_t bytes = (uint32_t)min(g.KC, K - k0) * 2u;
+                                    mbar_expect_tx(&full_bar[stage], 2 * bytes);
+                                    bulk_load_1d(dst, W + (size_t)(2 * pair0) * K + k0, bytes, &full_bar[stage]);
+                                    bulk_load_1d(dst + (size_t)g.KC * 2, W + (size_t)(2 * pair0 + 1) * K + k0, bytes, &full_bar[stage]);
+                                }
+                            }
+                            if (++stage == n_stages) { stage = 0; phase ^= 1; }
+                        }
+            }
+            // every load of this CTA is issued: queue L2 prefetches of this CTA's slice of the NEXT launch's first weights
+            if (alive && p.pf_bytes) {
+                const unsigned long long per = ((p.pf_bytes / gridDim.x) + 4095ull) & ~4095ull;
+                unsigned long long off = (unsigned long long)blockIdx.x * per;
+                const unsigned long long end = off + per < p.pf_bytes ? off + per : p.pf_bytes;
+                for (; off < end; off += 16384ull) {
+                    const uint32_t sz = (uint32_t)(end - off < 16384ull ? end - off : 16384ull);
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.pf_ptr + off), "r"(sz) : "memory");
+                }
+            }
+        }
+        return;
+    }
+
+    // ===================================================================== consumers (256 threads)
+    unsigned* const bar_ctr = p.sync;
+    unsigned* const err_word = p.sync + 2;
+    unsigned* const grp_ctr = p.sync + 4;
+    unsigned bar_target = 0;
+    // One dependency: `n_arrivals` publishers (this CTA is one of them iff `arrive`), every CTA waits for all of them.
+    // Returns false when the wait timed out (the CTA then leaves the job loop; the host sees the error word).
+    auto grid_dep = [&](bool arrive, unsigned n_arrivals) -> bool {
+        dc_bar(1, DC_CT);                              // every consumer thread's stores of this job are issued
+        if (tid == 0) {
+            if (arrive) {
+                __threadfence();
+                dc_red_release(bar_ctr, 1u);
+            }
+            bar_target += n_arrivals;
+            unsigned long long t0 = 0;
+            int it = 0;
+            while ((int)(dc_ld_acquire(bar_ctr) - bar_target) < 0) {
+                if (((++it) & 0x3ff) == 0) {
+                    const unsigned long long now = dc_timer();
+                    if (!t0) t0 = now;
+                    if (now - t0 > DC_TIMEOUT_NS || dc_ld_acquire(err_word)) {
+                        atomicExch(err_word, 1u);
+                        s_dead = 1;
+                        break;
+                    }
+                }
+            }
+        }
+        dc_bar(1, DC_CT);
+        return s_dead == 0;
+    };
+    int seq = warp;     // this warp's next ring sequence number (advances by NW per stage, only for warp < NW)
+
+    // activations come from the previous kernel: wait for it (no-op without the PDL attribute); the producer warp
+    // above streams weights, which nobody writes, without waiting
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    for (int j = 0; j < p.n_jobs; ++j) {
+        const tl_decode_job& jb = p.jobs[j];
+        const bool last_job = j == p.n_jobs - 1;
+        if (jb.type == TL_JOB_GEMV) {
+            const int N = jb.N, K = jb.K, flags = jb.flags;
+            const bf16* x = reinterpret_cast<const bf16*>(jb.x);
+            bf16* y = reinterpret_cast<bf16*>(jb.y);
+            const bf16* bias = reinterpret_cast<const bf16*>(jb.bias);
+            const bf16* residual = reinterpret_cast<const bf16*>(jb.residual);
+            const bf16* norm_w = reinterpret_cast<const bf16*>(jb.norm_w);
+            const float eps = jb.eps;
+            const int nvec = K >> 3;
+            // ---- stage x (possibly written by other CTAs in the previous job: L2-coherent loads), one global pass
+            if (norm_w) {
+                float ss[M];
+#pragma unroll
+                for (int m = 0; m < M; ++m) ss[m] = 0.f;
+                for (int v = tid; v < nvec; v += DC_CT) {
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        const uint4 u = dc_ldcg_v4(x + (size_t)m * K + (size_t)v * 8);
+                        reinterpret_cast<uint4*>(xs + (size_t)m * K)[v] = u;
+                        const uint32_t* u32 = reinterpret_cast<const uint32_t*>(&u);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float a = bf16_lo(u32[q]), b = bf16_hi(u32[q]);
+                            ss[m] += a * a + b * b;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    const float t = warp_sum(ss[m]);
+                    if (lane == 0) s_part[warp][m] = t;
+                }
+                dc_bar(1, DC_CT);
+                float rstd[M];
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    float t = 0.f;
+#pragma unroll
+                    for (int w = 0; w < DC_CW; ++w) t += s_part[w][m];
+                    rstd[m] = 1.0f / sqrtf(t / (float)K + eps);
+                }
+                for (int v = tid; v < nvec; v += DC_CT) {          // each thread re-reads exactly what it wrote
+                    const uint4 g = reinterpret_cast<const uint4*>(norm_w)[v];
+                    const uint32_t* g32 = reinterpret_cast<const uint32_t*>(&g);
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        const uint4 u = reinterpret_cast<const uint4*>(xs + (size_t)m * K)[v];
+                        uint4 o;
+                        const uint32_t* u32 = reinterpret_cast<const uint32_t*>(&u);
+                        uint32_t* o32 = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            o32[q] = pack_bf16(bf16_lo(g32[q]) * rbf(bf16_lo(u32[q]) * rstd[m]),
+                                               bf16_hi(g32[q]) * rbf(bf16_hi(u32[q]) * rstd[m]));
+                        reinterpret_cast<uint4*>(xs + (size_t)m * K)[v] = o;
+                    }
+                }
+            } else {
+                for (int v = tid; v < nvec * M; v += DC_CT)
+                    reinterpret_cast<uint4*>(xs)[v] = dc_ldcg_v4(x + (size_t)v * 8);
+            }
+            dc_bar(1, DC_CT);
+
+            const DcGeom g = dc_geom(N, K, NW);
+            const bool swiglu = flags & TL_EPI_SWIGLU;
+            const int n_out = swiglu ? g.npairs : N;
+            auto finish = [&](int pair, const float (&a0)[M], const float (&a1)[M]) {
+                if (lane != 0) return;
+                const int r0 = 2 * pair;
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    float v0 = a0[m], v1 = a1[m];
+                    if (flags & TL_EPI_BIAS) {
+                        v0 += bf2f(bias[r0]);
+                        v1 += bf2f(bias[r0 + 1]);
+                    }
+                    if (swiglu) {
+                        const float gate = rbf(v0), up = rbf(v1);
+                        y[(size_t)m * n_out + pair] = f2bf(rbf(silu_f(gate)) * up);
+                    } else {
+                        float t0 = rbf(v0), t1 = rbf(v1);
+                        if (flags & TL_EPI_RESIDUAL) {
+                            t0 += dc_ldcg_bf16(residual + (size_t)m * N + r0);
+                            t1 += dc_ldcg_bf16(residual + (size_t)m * N + r0 + 1);
+                        }
+                        *reinterpret_cast<uint32_t*>(y + (size_t)m * N + r0) = pack_bf16(t0, t1);
+                    }
+                }
+            };
+            auto dot2 = [&](const uint4* r0, const uint4* r1, int k0, int vecs, float (&a0)[M], float (&a1)[M]) {
+#pragma unroll 4
+                for (int v = lane; v < vecs; v += 32) {
+                    const uint4 w0 = r0[v], w1 = r1[v];
+                    const uint32_t* a32 = reinterpret_cast<const uint32_t*>(&w0);
+                    const uint32_t* b32 = reinterpret_cast<const uint32_t*>(&w1);
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        const uint4 xv = reinterpret_cast<const uint4*>(xs + (size_t)m * K + k0)[v];
+                        const uint32_t* x32 = reinterpret_cast<const uint32_t*>(&xv);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float xl = bf16_lo(x32[q]), xh = bf16_hi(x32[q]);
+                            a0[m] = fmaf(bf16_lo(a32[q]), xl, a0[m]);
+                            a0[m] = fmaf(bf16_hi(a32[q]), xh, a0[m]);
+                            a1[m] = fmaf(bf16_lo(b32[q]), xl, a1[m]);
+                            a1[m] = fmaf(bf16_hi(b32[q]), xh, a1[m]);
+                        }
+                    }
+                }
+            };
+            if (warp < NW) {
+                for (int gi = 0; gi < g.n_groups; ++gi) {
+                    const int unit = gi * NW + warp;
+                    const bool valid = unit < g.n_units;
+                    const int pair0 = g.p_begin + unit * g.P;
+                    float a0[M], a1[M];
+#pragma unroll
+                    for (int m = 0; m < M; ++m) a0[m] = a1[m] = 0.f;
+                    for (int c = 0; c < g.n_chunks; ++c, seq += NW) {
+                        const int stage = seq % n_stages;
+                        const uint32_t phase = (uint32_t)(seq / n_stages) & 1u;
+                        mbar_wait(&full_bar[stage], phase);
+                        const unsigned char* src = ring + (size_t)stage * DC_STAGE;
+                        if (valid) {
+                            if (!g.chunked) {
+                                const int np = min(g.P, g.p_end - pair0);
+                                for (int pp = 0; pp < np; ++pp) {
+                                    float b0[M], b1[M];
+#pragma unroll
+                                    for (int m = 0; m < M; ++m) b0[m] = b1[m] = 0.f;
+                                    dot2(reinterpret_cast<const uint4*>(src + (size_t)(2 * pp) * K * 2),
+                                         reinterpret_cast<const uint4*>(src + (size_t)(2 * pp + 1) * K * 2), 0, nvec, b0, b1);
+#pragma unroll
+                                    for (int m = 0; m < M; ++m) { b0[m] = warp_sum(b0[m]); b1[m] = warp_sum(b1[m]); }
+                                    finish(pair0 + pp, b0, b1);
+                                }
+                            } else {
+                                const int k0 = c * g.KC;
+                                dot2(reinterpret_cast<const uint4*>(src), reinterpret_cast<const uint4*>(src + (size_t)g.KC * 2), k0,
+                                     min(g.KC, K - k0) >> 3, a0, a1);
+                            }
+                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+                    }
+                    if (valid && g.chunked) {
+#pragma unroll
+                        for (int m = 0; m < M; ++m) { a0[m] = warp_sum(a0[m]); a1[m] = warp_sum(a1[m]); }
+                        finish(pair0, a0, a1);
+                    }
+                }
+            }
+            if (!last_job && !grid_dep(true, gridDim.x)) break;
+        } else if (jb.type == TL_JOB_ATTN) {
+            // ---- RoPE (+ q/k norm) + KV append + split-KV attention over all CTAs, one (row, kv head) group at a time
+            const int n_h = jb.n_h, n_kv = jb.n_kv, D = jb.d, T_max = jb.T_max;
+            const int HALF = D >> 1, n_rep = n_h / n_kv, cap = p.chunk_cap;
+            const int G = n_kv * M;
+            const int cpg = (int)gridDim.x / G;                       // CTAs per group (>= 1, checked on the host)
+            const int grp = (int)blockIdx.x / cpg, split = (int)blockIdx.x % cpg;
+            const bool in_grid = grp < G;
+            const int b = in_grid ? grp / n_kv : 0, kvh = in_grid ? grp % n_kv : 0;
+            const int pos = reinterpret_cast<const int32_t*>(jb.pos_dev)[(jb.flags & TL_ATTN_POS_PER_ROW) ? b : 0];
+            const int n_keys = pos + 1;                               // cached keys 0..pos-1 + the new token
+            int cpg_eff = min(cpg, (n_keys + DC_MIN_KEYS - 1) / DC_MIN_KEYS);
+            const int chunk = (n_keys + cpg_eff - 1) / cpg_eff;
+            cpg_eff = (n_keys + chunk - 1) / chunk;                   // no empty ranges
+            const bool active = in_grid && split < cpg_eff;
+            float* sq = attn_s;                       // [8][128]
+            float* sk = sq + 8 * 128;                 // [128]
+            float* sv = sk + 128;                     // [128]
+            float* so = sv + 128;                     // [8][128]
+            float* sred = so + 8 * 128;               // [64]
+            float* sml = sred + 64;                   // [16]  (m, l) per query head
+            float* sc = sml + 16;                     // [n_rep][cap] scores / probabilities
+            if (tid == 0) s_last = 0;
+            if (active) {
+                const int k0 = split * chunk, k1 = min(n_keys, k0 + chunk);
+                const bool owns_pos = k1 == n_keys;
+                const int nk = k1 - k0, nk_cached = owns_pos ? nk - 1 : nk;
+                const int heads = n_h + 2 * n_kv;
+                const bf16* row = reinterpret_cast<const bf16*>(jb.x) + (size_t)b * heads * D;
+                const bf16* cos_tab = reinterpret_cast<const bf16*>(jb.cos_tab);
+                const bf16* sin_tab = reinterpret_cast<const bf16*>(jb.sin_tab);
+                const bf16* qn = reinterpret_cast<const bf16*>(jb.q_norm_w);
+                const bf16* kn = reinterpret_cast<const bf16*>(jb.k_norm_w);
+                bf16* k_cache = reinterpret_cast<bf16*>(jb.k_cache);
+                bf16* v_cache = reinterpret_cast<bf16*>(jb.v_cache);
+                // -- A: q of the n_rep heads (warp u), k of the new token (warp n_rep) -> norm -> RoPE -> shared memory
+                for (int u = warp; u <= n_rep; u += DC_CW) {
+                    const bool is_k = u == n_rep;
+                    if (is_k && !owns_pos) continue;
+                    const bf16* src = row + (size_t)(is_k ? n_h + kvh : kvh * n_rep + u) * D;
+                    const bf16* nw = is_k ? kn : qn;
+                    float* dst = is_k ? sk : sq + u * 128;
+                    float x1[2], x2[2];
+                    float ssq = 0.f;
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        const int i = lane + 32 * t;
+                        x1[t] = x2[t] = 0.f;
+                        if (i < HALF) {
+                            x1[t] = dc_ldcg_bf16(src + i);
+                            x2[t] = dc_ldcg_bf16(src + i + HALF);
+                            ssq += x1[t] * x1[t] + x2[t] * x2[t];
+                        }
+                    }
+                    if (nw) {
+                        const float r = 1.0f / sqrtf(warp_sum(ssq) / (float)D + jb.eps);
+#pragma unroll
+                        for (int t = 0; t < 2; ++t) {
+                            const int i = lane + 32 * t;
+                            if (i < HALF) {
+                                x1[t] = rbf(bf2f(nw[i]) * rbf(x1[t] * r));
+                                x2[t] = rbf(bf2f(nw[i + HALF]) * rbf(x2[t] * r));
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        const int i = lane + 32 * t;
+                        if (i < HALF) {
+                            const float c = bf2f(cos_tab[(size_t)pos * HALF + i]), s = bf2f(sin_tab[(size_t)pos * HALF + i]);
+                            dst[i] = rbf(rbf(x1[t] * c) + rbf(-x2[t] * s));
+                            dst[i + HALF] = rbf(rbf(x2[t] * c) + rbf(x1[t] * s));
+                        }
+                    }
+                }
+                if (owns_pos && tid < D) sv[tid] = dc_ldcg_bf16(row + (size_t)(n_h + n_kv + kvh) * D + tid);
+                dc_bar(1, DC_CT);
+                if (owns_pos && tid < D) {                       // append the new key / value to the cache
+                    const size_t off = (((size_t)b * n_kv + kvh) * T_max + pos) * D + tid;
+                    k_cache[off] = f2bf(sk[tid]);
+                    v_cache[off] = f2bf(sv[tid]);
+                }
+                const bf16* kb = k_cache + ((size_t)b * n_kv + kvh) * T_max * D;
+                const bf16* vb = v_cache + ((size_t)b * n_kv + kvh) * T_max * D;
+                const float scale_log2 = jb.scale * 1.4426950408889634f;
+                // -- B: scores.  4 threads share a cached key (a quarter of the head dim each), all n_rep heads at once
+                {
+                    const int part = tid & 3, EP = D >> 2;
+                    for (int base = 0; base < nk_cached; base += DC_CT / 4) {
+                        const int kl = base + (tid >> 2);
+                        const bool ok = kl < nk_cached;
+                        float acc[8];
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+                        if (ok) {
+                            const uint4* kr = reinterpret_cast<const uint4*>(kb + (size_t)(k0 + kl) * D + part * EP);
+                            for (int c = 0; c < (EP >> 3); ++c) {
+                                const uint4 kv4 = kr[c];
+                                const uint32_t* k32 = reinterpret_cast<const uint32_t*>(&kv4);
+                                const float f0 = bf16_lo(k32[0]), f1 = bf16_hi(k32[0]), f2 = bf16_lo(k32[1]), f3 = bf16_hi(k32[1]);
+                                const float f4 = bf16_lo(k32[2]), f5 = bf16_hi(k32[2]), f6 = bf16_lo(k32[3]), f7 = bf16_hi(k32[3]);
+#pragma unroll
+                                for (int r = 0; r < 8; ++r) {
+                                    if (r < n_rep) {
+                                        const float4 qa = *reinterpret_cast<const float4*>(&sq[r * 128 + part * EP + c * 8]);
+                                        const float4 qb = *reinterpret_cast<const float4*>(&sq[r * 128 + part * EP + c * 8 + 4]);
+                                        acc[r] += f0 * qa.x + f1 * qa.y + f2 * qa.z + f3 * qa.w + f4 * qb.x + f5 * qb.y + f6 * qb.z + f7 * qb.w;
+                                    }
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) {
+                            if (r < n_rep) {
+                                float v = acc[r];
+                                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                                if (ok && part == 0) sc[r * cap + kl] = v * scale_log2;
+                            }
+                        }
+                    }
+                    if (owns_pos) {                              // the new token's key comes from shared memory
+                        for (int r = warp; r < n_rep; r += DC_CW) {
+                            float acc = 0.f;
+                            for (int i = lane; i < D; i += 32) acc += sq[r * 128 + i] * sk[i];
+                            acc = warp_sum(acc) * scale_log2;
+                            if (lane == 0) sc[r * cap + nk - 1] = acc;
+                        }
+                    }
+                }
+                dc_bar(1, DC_CT);
+                // -- C: per-head softmax over this CTA's key range (P rounded to bf16 before P.V: SDPA contract)
+                for (int r = warp; r < n_rep; r += DC_CW) {
+                    float mx = -INFINITY;
+                    for (int kl = lane; kl < nk; kl += 32) mx = fmaxf(mx, sc[r * cap + kl]);
+                    mx = warp_max(mx);
+                    float l = 0.f;
+                    for (int kl = lane; kl < nk; kl += 32) {
+                        const float pr = exp2f(sc[r * cap + kl] - mx);
+                        l += pr;
+                        sc[r * cap + kl] = rbf(pr);
+                    }
+                    l = warp_sum(l);
+                    if (lane == 0) { sml[2 * r] = mx; sml[2 * r + 1] = l; }
+                }
+                dc_bar(1, DC_CT);
+                // -- D: P.V.  wph warps per head share the keys; a lane owns D/32 output dims
+                {
+                    const int wph = max(1, DC_CW / n_rep), r = warp / wph, sub = warp % wph;
+                    if (r < n_rep) {
+                        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                        if (D == 128) {
+                            for (int kl = sub; kl < nk_cached; kl += wph) {
+                                const uint2 vv = *reinterpret_cast<const uint2*>(vb + (size_t)(k0 + kl) * D + lane * 4);
+                                const float pr = sc[r * cap + kl];
+                                acc[0] = fmaf(pr, bf16_lo(vv.x), acc[0]);
+                                acc[1] = fmaf(pr, bf16_hi(vv.x), acc[1]);
+                                acc[2] = fmaf(pr, bf16_lo(vv.y), acc[2]);
+                                acc[3] = fmaf(pr, bf16_hi(vv.y), acc[3]);
+                            }
+                            if (owns_pos && sub == 0) {
+                                const float pr = sc[r * cap + nk - 1];
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) acc[q] = fmaf(pr, sv[lane * 4 + q], acc[q]);
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) so[(sub * n_rep + r) * 128 + lane * 4 + q] = acc[q];
+                        } else {   // D == 64
+                            for (int kl = sub; kl < nk_cached; kl += wph) {
+                                const uint32_t vv = *reinterpret_cast<const uint32_t*>(vb + (size_t)(k0 + kl) * D + lane * 2);
+                                const float pr = sc[r * cap + kl];
+                                acc[0] = fmaf(pr, bf16_lo(vv), acc[0]);
+                                acc[1] = fmaf(pr, bf16_hi(vv), acc[1]);
+                            }
+                            if (owns_pos && sub == 0) {
+                                const float pr = sc[r * cap + nk - 1];
+                                acc[0] = fmaf(pr, sv[lane * 2], acc[0]);
+                                acc[1] = fmaf(pr, sv[lane * 2 + 1], acc[1]);
+                            }
+                            so[(sub * n_rep + r) * 128 + lane * 2] = acc[0];
+                            so[(sub * n_rep + r) * 128 + lane * 2 + 1] = acc[1];
+                        }
+                    }
+                }
+                dc_bar(1, DC_CT);
+                // -- E: publish this CTA's partial (o unnormalised, m, l) per query head
+                {
+                    const int wph = max(1, DC_CW / n_rep);
+                    for (int idx = tid; idx < n_rep * D; idx += DC_CT) {
+                        const int r = idx / D, dd = idx % D;
+                        float o = 0.f;
+                        for (int s = 0; s < wph; ++s) o += so[(s * n_rep + r) * 128 + dd];
+                        p.attn_part[(((size_t)b * n_h + kvh * n_rep + r) * cpg + split) * (D + 2) + dd] = o;
+                    }
+                    if (tid < n_rep) {
+                        float* pp = p.attn_part + (((size_t)b * n_h + kvh * n_rep + tid) * cpg + split) * (D + 2) + D;
+                        pp[0] = sml[2 * tid];
+                        pp[1] = sml[2 * tid + 1];
+                    }
+                }
+                dc_bar(1, DC_CT);
+                if (tid == 0) {
+                    __threadfence();
+                    const unsigned old = atomicAdd(&grp_ctr[grp], 1u);
+                    if (old == (unsigned)(cpg_eff - 1)) {
+                        __threadfence();
+                        s_last = 1;
+                    }
+                }
+                dc_bar(1, DC_CT);
+                if (s_last) {
+                    // -- F: the last CTA of the group combines the partials of all key ranges and writes the attention
+                    //       output of its n_rep heads; then the group counter is ready for the next launch
+                    for (int idx = tid; idx < n_rep * D; idx += DC_CT) {
+                        const int r = idx / D, dd = idx % D, h = kvh * n_rep + r;
+                        const float* base = p.attn_part + ((size_t)b * n_h + h) * cpg * (D + 2);
+                        float m = -INFINITY;
+                        for (int s = 0; s < cpg_eff; ++s) m = fmaxf(m, __ldcg(base + (size_t)s * (D + 2) + D));
+                        float L = 0.f, O = 0.f;
+                        for (int s = 0; s < cpg_eff; ++s) {
+                            const float w = exp2f(__ldcg(base + (size_t)s * (D + 2) + D) - m);
+                            L = fmaf(w, __ldcg(base + (size_t)s * (D + 2) + D + 1), L);
+                            O = fmaf(w, __ldcg(base + (size_t)s * (D + 2) + dd), O);
+                        }
+                        reinterpret_cast<bf16*>(jb.y)[((size_t)b * n_h + h) * D + dd] = f2bf(O / L);
+                    }
+                    if (tid == 0) grp_ctr[grp] = 0u;
+                }
+            }
+            // one arrival per (row, kv head) group, by the CTA that combined it; everybody waits for all groups
+            if (!last_job && !grid_dep(s_last != 0, (unsigned)G)) break;
+        }
+    }
+    // ---- self-cleaning: the last CTA to leave resets the counters for the next launch on this sync slot
+    dc_bar(1, DC_CT);
+    if (tid == 0) {            // (a producer parked on an empty-slot wait polls s_dead and leaves by itself)
+        __threadfence();
+        const unsigned prev = atomicAdd(&p.sync[1], 1u);
+        if (prev == gridDim.x - 1) {
+            p.sync[0] = 0;
+            p.sync[1] = 0;
+            __threadfence();
+        }
+    }
+}
+
+}  // namespace tl
+
+extern "C" {
+
+size_t tl_decode_chain_ws(int M, int n_h, int n_kv, int d) {
+    // attention partials [M*n_h][cpg][d+2] floats with cpg = CTAs / (n_kv*M) <= 160 / (n_kv*M) on any sm_100 part
+    if (M < 1 || n_h < 1 || n_kv < 1) return 0;
+    const int cpg = 160 / (n_kv * M) > 0 ? 160 / (n_kv * M) : 1;
+    return (size_t)M * n_h * cpg * (d + 2) * sizeof(float) + 256;
+}
+
+int tl_decode_chain(const tl_decode_job* jobs, int n_jobs, int M, void* sync_slot, void* attn_ws, size_t attn_ws_bytes,
+                    const void* pf_ptr, size_t pf_bytes, void* stream) {
+    using namespace tl;
+    TL_REQUIRE(M >= 1 && M <= DC_MAX_M, TL_ERR_INVALID, "tl_decode_chain: M=%d outside 1..%d", M, DC_MAX_M);
+    TL_REQUIRE(jobs && n_jobs > 0 && n_jobs <= DC_MAX_JOBS && sync_slot, TL_ERR_INVALID, "tl_decode_chain: bad job list (n=%d, max %d)",
+               n_jobs, DC_MAX_JOBS);
+    const int grid = sm_count();
+    int k_max = 0, chunk_cap = 0, n_attn = 0;
+    for (int j = 0; j < n_jobs; ++j) {
+        const tl_decode_job& jb = jobs[j];
+        if (jb.type == TL_JOB_GEMV) {
+            TL_REQUIRE(jb.K % 8 == 0 && jb.N % 2 == 0 && jb.N > 0 && (((uintptr_t)jb.W) & 15) == 0, TL_ERR_INVALID,
+                       "tl_decode_chain: job %d bad GEMV shape / alignment", j);
+            if (jb.K > k_max) k_max = jb.K;
+        } else if (jb.type == TL_JOB_ATTN) {
+            TL_REQUIRE((jb.d == 64 || jb.d == 128) && jb.n_kv > 0 && jb.n_h % jb.n_kv == 0 && jb.n_h / jb.n_kv <= 8, TL_ERR_INVALID,
+                       "tl_decode_chain: job %d attention shape unsupported (d=%d n_h=%d n_kv=%d)", j, jb.d, jb.n_h, jb.n_kv);
+            const int G = jb.n_kv * M;
+            TL_REQUIRE(G <= grid && G <= 60, TL_ERR_INVALID, "tl_decode_chain: %d (row, kv head) groups do not fit", G);
+            const int cpg = grid / G;
+            const int cap = max(DC_MIN_KEYS, (jb.T_max + cpg - 1) / cpg);
+            if (cap > chunk_cap) chunk_cap = cap;
+            TL_REQUIRE(attn_ws && attn_ws_bytes >= (size_t)M * jb.n_h * cpg * (jb.d + 2) * sizeof(float), TL_ERR_INVALID,
+                       "tl_decode_chain: attention workspace too small");
+            ++n_attn;
+        } else {
+            TL_REQUIRE(false, TL_ERR_INVALID, "tl_decode_chain: job %d has unsupported type %d", j, jb.type);
+        }
+    }
+    chunk_cap = (chunk_cap + 3) & ~3;
+    constexpr int SMEM_CAP = 227 * 1024 - 1024;       // static shared memory of the kernel stays below 1 KB
+    const size_t xs_bytes = (((size_t)M * k_max * 2) + 127) & ~(size_t)127;
+    const size_t attn_bytes = (size_t)(DC_ATTN_FIXED + 8 * chunk_cap) * sizeof(float);
+    const size_t fixed = xs_bytes + attn_bytes + 2 * DC_MAX_STAGES * sizeof(uint64_t);
+    TL_REQUIRE(fixed + 4 * DC_STAGE <= (size_t)SMEM_CAP, TL_ERR_INVALID, "tl_decode_chain: M*K_max / context too large (%zu B fixed)", fixed);
+    int max_stages = (int)((SMEM_CAP - fixed) / DC_STAGE);
+    if (max_stages > DC_MAX_STAGES) max_stages = DC_MAX_STAGES;
+    int n_stages = 0, NW = 0;
+    for (int nw = DC_CW; nw >= 4; --nw) {
+        const int s = max_stages / nw * nw;
+        if (s > n_stages) { n_stages = s; NW = nw; }
+    }
+    ChainParams prm = {};
+    prm.n_jobs = n_jobs;
+    prm.n_stages = n_stages;
+    prm.NW = NW;
+    prm.xs_bytes = (int)xs_bytes;
+    prm.chunk_cap = chunk_cap;
+    prm.sync = (unsigned*)sync_slot;
+    prm.attn_part = (float*)attn_ws;
+    prm.pf_ptr = (const unsigned char*)pf_ptr;
+    prm.pf_bytes = (((uintptr_t)pf_ptr) & 15) ? 0ull : (unsigned long long)(pf_bytes & ~(size_t)15);
+    for (int j = 0; j < n_jobs; ++j) prm.jobs[j] = jobs[j];
+    const size_t smem = (size_t)n_stages * DC_STAGE + fixed;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(DC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static int use_pdl = -1;
+    if (use_pdl < 0) {
+        const char* e = getenv("TL_PDL");
+        use_pdl = (e && e[0] == '0') ? 0 : 1;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = use_pdl ? 1 : 0;
+#define TL_DC_LAUNCH(MM)                                                                                                   \
+    {                                                                                                                      \
+        static bool done = false;                                                                                          \
+        if (!done) {                                                                                                       \
+            if (cudaFuncSetAttribute(decode_chain_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAP) != cudaSuccess) \
+                return check_launch("tl_decode_chain (smem attr)");                                                      \
+            done = true;                                                                                                   \
+        }                                                                                                                  \
+        cudaLaunchKernelEx(&cfg, decode_chain_kernel<MM>, prm);                                                            \
+    }
+    switch (M) {
+        case 1: TL_DC_LAUNCH(1) break;
+        case 2: TL_DC_LAUNCH(2) break;
+        case 3: TL_DC_LAUNCH(3) break;
+        default: TL_DC_LAUNCH(4) break;
+    }
+#undef TL_DC_LAUNCH
+    return check_launch("tl_decode_chain");
+}
+
+}  // extern "C"

@@ -300,6 +300,8 @@ class DistributedModel(torch.nn.Module):
                 streamer.put(ring.out_log[:n_mb, :b, step].reshape(-1).cpu())
         torch.cuda.synchronize(dev)
         ring.check()
+        if hasattr(st, "check"):
+            st.check()
         if profile:
             self.timers["decode_span_s"] = span[0].elapsed_time(span[1]) * 1e-3
             self.timers["decode_busy_s"] = self.timers["decode_span_s"] - float(ring.wait_ns.item()) * 1e-9
@@ -351,6 +353,10 @@ class DistributedModel(torch.nn.Module):
         # ---- prefill every micro-batch through the pipeline; the last stage produces the first new token
         multi = self.world > 1
         ring = self._peer_ring(n_mb) if multi else None
+        if multi and ring is None and hasattr(st, "slots"):
+            for g in st.slots:                       # NCCL kernels share the SMs during decode: no persistent all-SM kernel
+                if hasattr(g, "allow_chain"):
+                    g.allow_chain = False
         if ring is not None:
             if max_new > ring.max_new:
                 raise ValueError(f"max_new_tokens {max_new} exceeds the token log of the peer ring ({ring.max_new})")
@@ -419,6 +425,8 @@ class DistributedModel(torch.nn.Module):
         else:
             result = torch.empty(B, S + max_new, dtype=torch.int64, device=dev)
         link.broadcast(result, 0)
+        if hasattr(st, "check"):
+            st.check()
         if streamer is not None and link.first:
             streamer.end()
         self.timers["generate_wall_s"] = time.perf_counter() - t0

@@ -227,6 +227,10 @@ class CudaLayerGroup:
         self.dec_ws = torch.empty(max(nat.attn_decode_ws(max_batch, cfg.n_heads, cfg.head_dim, max_seq), 16),
                                   dtype=torch.uint8, device=dev)
         self.scale = cfg.head_dim ** -0.5
+        self.allow_chain = True              # DistributedModel clears it when NCCL kernels share the device during decode
+        self.chain_sync: Optional[torch.Tensor] = None
+        self.chain_attn_ws: Optional[torch.Tensor] = None
+        self._chains: Dict[tuple, list] = {}
 
     def _make_bufs(self, n: int) -> ShardBuffers:
         cfg, dev, bf = self.cfg, self.device, torch.bfloat16
@@ -347,6 +351,11 @@ class CudaLayerGroup:
         w = self._dbufs(B)
         if advance:
             nat.advance_pos(self.kvlen_dev, None, 1)
+        if self.chain_ok(B):
+            self._decode_step_chained(x, B, out)
+            if advance:
+                nat.advance_pos(self.pos_dev, None, 1)
+            return
         for j in range(self.num_layers):
             o = out if j == self.num_layers - 1 else None
             if B <= gemv_max_rows():
@@ -356,27 +365,81 @@ class CudaLayerGroup:
         if advance:
             nat.advance_pos(self.pos_dev, None, 1)
 
-    def decode_jobs(self, x: torch.Tensor, B: int) -> list:
-        """The layer part of a decode step as ``tl_decode_job`` entries (x [B,H] updated in place)."""
+    # ------------------------------------------------------------------------------------------ chained decode step
+    def chain_ok(self, B: int) -> bool:
+        """Rows / shapes the persistent chain kernel (csrc/decode_chain.cu) takes; TL_DECODE_IMPL=kernels forces the
+        per-kernel launch sequence."""
+        import os
+        cfg = self.cfg
+        return (os.environ.get("TL_DECODE_IMPL", "chain") == "chain" and self.allow_chain and self.num_layers > 0
+                and B <= min(4, gemv_max_rows()) and cfg.n_kv_heads * B <= 60 and cfg.n_heads // cfg.n_kv_heads <= 8
+                and cfg.head_dim in (64, 128))
+
+    def _chain_group(self) -> int:
+        """Decoder layers per chain launch (TL_CHAIN_LAYERS, default 1; 5 jobs per layer, at most 3 layers)."""
+        import os
+        return max(1, min(3, int(os.environ.get("TL_CHAIN_LAYERS", "1"))))
+
+    def _decode_chains(self, x: torch.Tensor, B: int, out: Optional[torch.Tensor]):
+        """The launch list of one decode step of this shard: qkv of the first layer as a stand-alone GEMV, then one
+        persistent launch per group of layers [ATTN, o, gate/up, down, qkv of the next layer]."""
+        key = (B, x.data_ptr(), 0 if out is None else out.data_ptr())
+        if key in self._chains:
+            return self._chains[key]
         cfg, v = self.cfg, self.p.v
         w = self._dbufs(B)
-        J = nat.DecodeJobList.job
-        jobs = []
-        for j, li in enumerate(self.layer_ids):
-            bq = v.get(f"l{li}.bqkv")
-            jobs.append(J(nat.JOB_GEMV, N=cfg.qkv_dim, K=cfg.hidden, flags=nat.EPI_BIAS if bq is not None else 0, W=v[f"l{li}.wqkv"],
-                          x=x, y=w.qkv, bias=bq, norm_w=v[f"l{li}.ln1"], eps=cfg.rms_eps))
-            jobs.append(J(nat.JOB_ATTN, x=w.qkv, y=w.attn, k_cache=self.kc[j], v_cache=self.vc[j], pos_dev=self.pos_dev,
-                          cos_tab=self.cos, sin_tab=self.sin, q_norm_w=v.get(f"l{li}.qn"), k_norm_w=v.get(f"l{li}.kn"),
-                          n_h=cfg.n_heads, n_kv=cfg.n_kv_heads, d=cfg.head_dim, T_max=self.T_max, scale=self.scale,
-                          eps=cfg.rms_eps))
-            jobs.append(J(nat.JOB_GEMV, N=cfg.hidden, K=cfg.q_dim, flags=nat.EPI_RESIDUAL, W=v[f"l{li}.wo"], x=w.attn, y=x,
-                          residual=x))
-            jobs.append(J(nat.JOB_GEMV, N=2 * cfg.intermediate, K=cfg.hidden, flags=nat.EPI_SWIGLU, W=v[f"l{li}.wgu"], x=x,
-                          y=w.act, norm_w=v[f"l{li}.ln2"], eps=cfg.rms_eps))
-            jobs.append(J(nat.JOB_GEMV, N=cfg.hidden, K=cfg.intermediate, flags=nat.EPI_RESIDUAL, W=v[f"l{li}.wd"], x=w.act,
-                          y=x, residual=x))
-        return jobs
+        J = nat.make_job
+        if self.chain_sync is None:
+            self.chain_sync = torch.zeros(self.num_layers + 1, nat.CHAIN_SYNC_BYTES // 4, dtype=torch.int32, device=self.device)
+            self.chain_attn_ws = torch.empty(nat.decode_chain_ws(min(self.B_max, 4), cfg.n_heads, cfg.n_kv_heads, cfg.head_dim),
+                                             dtype=torch.uint8, device=self.device)
+        per = self._chain_group()
+        launches = []
+        for g0 in range(0, self.num_layers, per):
+            jobs = []
+            g1 = min(self.num_layers, g0 + per)
+            for j in range(g0, g1):
+                li = self.layer_ids[j]
+                jobs.append(J(nat.JOB_ATTN, x=w.qkv, y=w.attn, k_cache=self.kc[j], v_cache=self.vc[j], pos_dev=self.pos_dev,
+                              cos_tab=self.cos, sin_tab=self.sin, q_norm_w=v.get(f"l{li}.qn"), k_norm_w=v.get(f"l{li}.kn"),
+                              n_h=cfg.n_heads, n_kv=cfg.n_kv_heads, d=cfg.head_dim, T_max=self.T_max, scale=self.scale,
+                              eps=cfg.rms_eps))
+                jobs.append(J(nat.JOB_GEMV, N=cfg.hidden, K=cfg.q_dim, flags=nat.EPI_RESIDUAL, W=v[f"l{li}.wo"], x=w.attn, y=x,
+                              residual=x))
+                jobs.append(J(nat.JOB_GEMV, N=2 * cfg.intermediate, K=cfg.hidden, flags=nat.EPI_SWIGLU, W=v[f"l{li}.wgu"], x=x,
+                              y=w.act, norm_w=v[f"l{li}.ln2"], eps=cfg.rms_eps))
+                last = j == self.num_layers - 1
+                jobs.append(J(nat.JOB_GEMV, N=cfg.hidden, K=cfg.intermediate, flags=nat.EPI_RESIDUAL, W=v[f"l{li}.wd"], x=w.act,
+                              y=(out if (last and out is not None) else x), residual=x))
+                if not last:
+                    ln = self.layer_ids[j + 1]
+                    bq = v.get(f"l{ln}.bqkv")
+                    jobs.append(J(nat.JOB_GEMV, N=cfg.qkv_dim, K=cfg.hidden, flags=nat.EPI_BIAS if bq is not None else 0,
+                                  W=v[f"l{ln}.wqkv"], x=x, y=w.qkv, bias=bq, norm_w=v[f"l{ln}.ln1"], eps=cfg.rms_eps))
+            # what the launch after this one streams first: the next group's o-projection, or whatever follows the shard
+            nxt = v[f"l{self.layer_ids[g1]}.wo"] if g1 < self.num_layers else self.weights_after_last_layer
+            launches.append(nat.DecodeChain(jobs, B, self.chain_sync[g0 // per], self.chain_attn_ws, nxt))
+        self._chains[key] = launches
+        return launches
+
+    def _decode_step_chained(self, x: torch.Tensor, B: int, out: Optional[torch.Tensor]):
+        cfg, v = self.cfg, self.p.v
+        w = self._dbufs(B)
+        l0 = self.layer_ids[0]
+        nat.gemv(x, v[f"l{l0}.wqkv"], out=w.qkv, bias=v.get(f"l{l0}.bqkv"), norm_w=v[f"l{l0}.ln1"], eps=cfg.rms_eps,
+                 next_w=v[f"l{l0}.wo"])
+        for ch in self._decode_chains(x, B, out):
+            ch.launch()
+
+    def n_chain_launches(self) -> int:
+        per = self._chain_group()
+        return 1 + (self.num_layers + per - 1) // per
+
+    def check(self):
+        """Raise if a chain launch gave up on a dependency wait (error word of its sync slot)."""
+        if self.chain_sync is not None and int(self.chain_sync[:, 2].max().item()):
+            self.chain_sync[:, :4].zero_()
+            raise nat.NativeError("decode chain kernel timed out waiting for a dependency (co-residency of its CTAs lost?)")
 
     # ------------------------------------------------------------------------------------------ reference-shaped API
     def forward(self, **kwargs) -> dict:

@@ -41,8 +41,6 @@ class CudaStage:
         self.x_dec = [torch.zeros(max_batch, cfg.hidden, dtype=torch.bfloat16, device=dev) for _ in range(n_slots)]
         self.ids_dec = [torch.zeros(max_batch, dtype=torch.int64, device=dev) for _ in range(n_slots)]
         self.graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
-        self.job_lists: Dict[tuple, object] = {}
-        self.step_ws = torch.zeros(nat.decode_step_ws(4), dtype=torch.uint8, device=dev)
         if has_head:
             self.head_ws = torch.empty(max(nat.lmhead_ws(min(max_batch, 8), cfg.vocab), max_batch * 64 * 8 + 256),
                                        dtype=torch.uint8, device=dev)
@@ -78,34 +76,6 @@ class CudaStage:
             nat.argmax_bf16(self.logits_dec[:B], ids_out, self.head_ws)
 
     # ------------------------------------------------------------------------------------------ decode step
-    def _use_step_kernel(self, B: int) -> bool:
-        """TL_DECODE_IMPL=step selects ONE persistent kernel per decode step (csrc/decode_step.cu: bit-identical,
-        measured 321 vs 343 tok/s at Qwen2.5-7B B=1 in round 1, so the per-kernel sequence under a CUDA graph with
-        programmatic dependent launches stays the default)."""
-        import os
-        g = self.slots[0]
-        return (os.environ.get("TL_DECODE_IMPL", "kernels") == "step" and B <= 4 and g.T_max <= g.FUSED_DECODE_MAX_T
-                and self.cfg.n_heads * B <= 148 and self.cfg.n_heads // self.cfg.n_kv_heads <= 8)
-
-    def _step_jobs(self, slot: int, B: int):
-        key = (slot, B)
-        if key not in self.job_lists:
-            cfg, v, grp = self.cfg, self.params.v, self.slots[slot]
-            J = nat.DecodeJobList.job
-            x = self.x_dec[slot][:B]
-            jobs = []
-            if self.has_embed:
-                jobs.append(J(nat.JOB_EMBED, N=cfg.vocab, K=cfg.hidden, W=v["embed"], x=self.ids_dec[slot], y=x))
-            jobs += grp.decode_jobs(x, B)
-            if self.has_head:
-                jobs.append(J(nat.JOB_GEMV, N=cfg.vocab, K=cfg.hidden, flags=0, W=v["head"], x=x, y=self.logits_dec,
-                              norm_w=v["norm"], eps=cfg.rms_eps))
-                jobs.append(J(nat.JOB_ARGMAX, N=cfg.vocab, x=self.logits_dec, y=self.ids_dec[slot],
-                              W=self.step_ws.data_ptr() + 64))
-            jobs.append(J(nat.JOB_ADVANCE, pos_dev=grp.pos_dev, y=grp.kvlen_dev))
-            self.job_lists[key] = nat.DecodeJobList(jobs, self.device)
-        return self.job_lists[key]
-
     def _decode_body_ring(self, slot: int, B: int, ring):
         """The decode step of a multi-stage pipeline with the hops on peer memory (p2p/peer.py): wait for this slot's
         input in the local mailbox, run the layers, let the last kernel store into the neighbour's mailbox, signal."""
@@ -129,9 +99,6 @@ class CudaStage:
     def _decode_body(self, slot: int, B: int, ring=None):
         if ring is not None:
             self._decode_body_ring(slot, B, ring)
-            return
-        if self._use_step_kernel(B):
-            nat.decode_step(self._step_jobs(slot, B), B, self.step_ws)
             return
         x = self.x_dec[slot][:B]
         if self.has_embed:
@@ -167,14 +134,19 @@ class CudaStage:
             self.graphs[key] = g
         g.replay()
 
+    def check(self):
+        for g in self.slots:
+            g.check()
+
     def n_decode_launches(self, B: int, ring: bool = False) -> int:
         """Kernel launches inside one decode step of this stage (for bench.py's gpu_launches claim)."""
-        if self._use_step_kernel(B):
-            return 1
         fused = self.slots[0].T_max <= self.slots[0].FUSED_DECODE_MAX_T
         gemv = B <= gemv_max_rows()
-        # GEMV path: 4 Linears + attention (1 fused / 3); batched: 4 GEMMs + 3 split-K reduce(+norm) passes + attention
-        n = len(self.slots[0].layer_ids) * ((7 if gemv else 10) - (2 if fused else 0)) + 2 + (0 if gemv else 1)
+        if self.slots[0].chain_ok(B):
+            n = self.slots[0].n_chain_launches() + 2       # qkv of the first layer + one persistent launch per layer group
+        else:
+            # GEMV path: 4 Linears + attention (1 fused / 3); batched: 4 GEMMs + 3 split-K reduce(+norm) passes + attention
+            n = len(self.slots[0].layer_ids) * ((7 if gemv else 10) - (2 if fused else 0)) + 2 + (0 if gemv else 1)
         if ring:
             n += (3 if self.has_embed else 2) - 2    # wait (+ token log) + signal, which also do the two position updates
         if self.has_embed:

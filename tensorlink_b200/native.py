@@ -48,8 +48,8 @@ _SIGS = {
     "tl_attn_decode_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int,
                                    c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "tl_attn_decode_fused": (c_int, [c_void_p] * 9 + [c_float, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
-    "tl_decode_step_ws": (c_size_t, [c_int]),
-    "tl_decode_step": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "tl_decode_chain_ws": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "tl_decode_chain": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
     "tl_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),
     "tl_peer_open": (c_int, [c_void_p, POINTER(c_void_p)]),
     "tl_peer_close": (c_int, [c_void_p]),
@@ -95,7 +95,9 @@ class DecodeJob(ctypes.Structure):
                 ("q_norm_w", c_void_p), ("k_norm_w", c_void_p), ("k_cache", c_void_p), ("v_cache", c_void_p)]
 
 
-JOB_GEMV, JOB_ATTN, JOB_EMBED, JOB_ARGMAX, JOB_ADVANCE = 0, 1, 2, 3, 4
+JOB_GEMV, JOB_ATTN = 0, 1
+ATTN_POS_PER_ROW = 1
+CHAIN_MAX_JOBS, CHAIN_SYNC_BYTES = 16, 1024
 
 _lib: Optional[ctypes.CDLL] = None
 
@@ -483,34 +485,39 @@ def attn_decode_fused(qkv, k_cache, v_cache, out, pos_dev, cos_tab, sin_tab, q_n
            "tl_attn_decode_fused")
 
 
-def decode_step_ws(M: int) -> int:
-    return int(load().tl_decode_step_ws(M))
+def decode_chain_ws(M: int, n_h: int, n_kv: int, d: int) -> int:
+    return int(load().tl_decode_chain_ws(M, n_h, n_kv, d))
 
 
-class DecodeJobList:
-    """Host + device copies of a ``tl_decode_job`` array (device copy owned by a torch uint8 tensor)."""
+def make_job(type_, **kw) -> DecodeJob:
+    j = DecodeJob()
+    j.type = type_
+    for k, v in kw.items():
+        if isinstance(v, torch.Tensor):
+            v = v.data_ptr()
+        setattr(j, k, v)
+    return j
 
-    def __init__(self, jobs, device):
-        self.n = len(jobs)
+
+class DecodeChain:
+    """One launch site of ``tl_decode_chain``: a host job array (kept alive here: a captured graph holds the parameter
+    copy, eager launches re-read this array), the rows per step, the private sync slot and the prefetch hint."""
+
+    def __init__(self, jobs, M: int, sync_slot: torch.Tensor, attn_ws: torch.Tensor, next_w: Optional[torch.Tensor] = None):
+        assert 1 <= len(jobs) <= CHAIN_MAX_JOBS
+        self.n, self.M = len(jobs), M
         self.host = (DecodeJob * self.n)(*jobs)
-        raw = bytes(self.host)
-        self.dev = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+        self.sync_slot, self.attn_ws, self.next_w = sync_slot, attn_ws, next_w
+        assert sync_slot.numel() * sync_slot.element_size() >= CHAIN_SYNC_BYTES
 
-    @staticmethod
-    def job(type_, **kw) -> DecodeJob:
-        j = DecodeJob()
-        j.type = type_
-        for k, v in kw.items():
-            if isinstance(v, torch.Tensor):
-                v = v.data_ptr()
-            setattr(j, k, v)
-        return j
-
-
-def decode_step(jobs: DecodeJobList, M: int, sync_ws: torch.Tensor):
-    require_device()
-    _check(load().tl_decode_step(_p(jobs.dev), ctypes.cast(jobs.host, c_void_p), jobs.n, M, _p(sync_ws), _stream()),
-           "tl_decode_step")
+    def launch(self):
+        require_device()
+        nb = 0
+        if self.next_w is not None and prefetch_bytes() > 0:
+            nb = min(self.next_w.numel() * self.next_w.element_size(), prefetch_bytes())
+        _check(load().tl_decode_chain(ctypes.cast(self.host, c_void_p), self.n, self.M, _p(self.sync_slot), _p(self.attn_ws),
+                                      self.attn_ws.numel() * self.attn_ws.element_size(), _p(self.next_w) if nb else None, nb,
+                                      _stream()), "tl_decode_chain")
 
 
 def qk_norm_bwd(qkv_pre, dqkv, qn, kn, dqn_acc, dkn_acc, eps, n_h, n_kv, d):

@@ -104,3 +104,78 @@ def test_apply_eos_matches_hf_generate_stopping():
             got = apply_eos(full, 6, eos, 0)
             assert got.shape == want.shape and torch.equal(got, want), eos
     assert torch.equal(apply_eos(full, 6), full)
+
+
+# ---------------------------------------------------------------------------------------------- the reference's planner
+def _golden_plans():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_plans.json")) as f:
+        return json.load(f)
+
+
+def _norm(x):
+    """JSON turns tuples into lists; compare structurally."""
+    if isinstance(x, (list, tuple)):
+        return [_norm(v) for v in x]
+    if isinstance(x, dict):
+        return {k: _norm(v) for k, v in x.items()}
+    return x
+
+
+def test_planner_restatement_equals_the_reference_planner():
+    """``graphing.create_distributed_config`` (memory estimate, greedy assignment, grouping) against plans produced by the
+    reference's own ``ModelParser`` (tests/golden/ref_plans.json, oracle/gen_golden_plans.py): same keys in the same
+    order, same workers, same layer ranges, memory to the last digit."""
+    import pytest
+    from tensorlink_b200.ml import graphing
+    from tensorlink_b200.ml.configs import get_config
+    for tag, g in _golden_plans().items():
+        got = graphing.create_distributed_config(get_config(g["model"]), {w: {"gpu_memory": m} for w, m in g["workers"].items()},
+                                                 trusted=False, **g["kwargs"])
+        assert got["success"], tag
+        assert got["model_memory"] == pytest.approx(g["model_memory"], rel=1e-12), tag
+        assert list(got["config"]) == list(g["config"]), tag
+        for k, want in g["config"].items():
+            have = _norm(got["config"][k])
+            assert set(have) == set(want), (tag, k, set(have) ^ set(want))
+            for f, v in want.items():
+                if f == "memory":
+                    assert have[f] == pytest.approx(v, rel=1e-12), (tag, k)
+                else:
+                    assert have[f] == v, (tag, k, f, have[f], v)
+
+
+def test_reference_plans_build_the_same_stages():
+    """A plan produced by the reference's planner (workers named by node-id hash strings, lm_head on a worker of its
+    own) is consumed as-is: workers map to pipeline ranks in plan order, every rank gets exactly the plan's layers."""
+    from tensorlink_b200.ml import graphing
+    for tag, g in _golden_plans().items():
+        plan = g["config"]
+        wr = graphing.worker_ranks(plan)
+        assert sorted(wr.values()) == list(range(len(wr))), tag
+        n = graphing.n_stages(plan)
+        covered = []
+        for rank in range(n):
+            layers = graphing.stage_layers(plan, rank)
+            assert layers == sorted(layers) and (not layers or layers == list(range(layers[0], layers[-1] + 1))), (tag, rank)
+            covered += layers
+            want = [i for k, e in plan.items() if e.get("type") == "offloaded_group" and wr[e["assigned_workers"][0]] == rank
+                    for i in range(e["layer_range"][0], e["layer_range"][1] + 1)]
+            assert layers == want, (tag, rank)
+        from tensorlink_b200.ml.configs import get_config
+        assert covered == list(range(get_config(g["model"]).n_layers)), tag
+    hashed = _golden_plans()["qwen25_7b_infer_hashed_workers"]["config"]
+    assert graphing.n_stages(hashed) == 2 and graphing.stage_layers(hashed, 0) == list(range(0, 14))
+
+
+def test_balanced_mode_and_failure():
+    from tensorlink_b200.ml import graphing
+    from tensorlink_b200.ml.configs import QWEN25_7B
+    workers = {f"w{i}": {"gpu_memory": 40e9} for i in range(4)}
+    bal = graphing.create_distributed_config(QWEN25_7B, {w: {"gpu_memory": 6e9} for w in workers}, training=False, max_seq_len=1024,
+                                             balanced=True)
+    sizes = [len(graphing.stage_layers(bal["config"], r)) for r in range(4)]
+    assert sizes == [len(r) for r in graphing.split_balanced(QWEN25_7B, 4)] and sum(sizes) == 28
+    tight = graphing.create_distributed_config(QWEN25_7B, {"a": {"gpu_memory": 2e9}}, training=False, max_seq_len=1024)
+    assert tight["success"] is False                        # like the reference: partial config, success False
