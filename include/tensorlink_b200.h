@@ -131,6 +131,16 @@ int tl_lmhead_argmax(const void* x, const void* W, const void* norm_w, float eps
 /* argmax over bf16 logits[M,V] (any M); workspace >= M*64*8 bytes */
 int tl_argmax_bf16(const void* logits, int64_t* ids_out, void* workspace, size_t ws_bytes, int M, int V, void* stream);
 
+/* ---- token sampling on the device (csrc/sample.cu): what HF `generate(do_sample=True)` does on the host's copy of the
+ * logits (the reference delegates to it, tensorlink/ml/module.py:763-769, ml/worker.py:403-404): temperature -> top-k
+ * (every logit >= the k-th largest is kept; 0 = off) -> top-p (a token is kept while the probability mass above it is
+ * < top_p; ties at the threshold are kept) -> one multinomial draw per row from Philox4x32-10(seed; row, counter).
+ * counters_dev: int32[M] in device memory, advanced by the kernel (a captured graph draws a fresh number per replay).
+ * workspace >= tl_sample_ws(M) bytes.  logits bf16 [M,V] row-major; ids_out int64[M]. */
+size_t tl_sample_ws(int M);
+int tl_sample(const void* logits, int64_t* ids_out, int M, int V, float temperature, int top_k, float top_p,
+              unsigned long long seed, int32_t* counters_dev, void* workspace, size_t ws_bytes, void* stream);
+
 /* ---- small device-side helpers used by the captured decode graph */
 int tl_advance_pos(int32_t* pos_dev, int32_t* kv_len_dev, int delta, void* stream); /* pos += delta; kv_len = pos */
 /* out_tokens[b, *step_dev] = ids[b] for b < B (row pitch ld), then ++*step_dev: the generated-token log
@@ -176,6 +186,10 @@ size_t tl_decode_chain_ws(int M, int n_h, int n_kv, int d);
  * optional L2 prefetch hint = the weights the NEXT launch streams first. */
 int tl_decode_chain(const tl_decode_job* jobs, int n_jobs, int M, void* sync_slot, void* attn_ws, size_t attn_ws_bytes,
                     const void* pf_ptr, size_t pf_bytes, void* stream);
+/* debugging aid: device buffer of n_slots * 2*(TL_DECODE_CHAIN_MAX_JOBS+1)*4 uint64; every later chain launch takes the
+ * next slot and stamps it with globaltimer values (CTA 0 and the last CTA; per job: start / input staged / work done /
+ * dependency passed; last row: kernel entry / previous grid done / exit); NULL = off */
+int tl_decode_chain_trace(void* buf, int n_slots);
 
 /* ---- peer-memory mailboxes: the inter-shard hop of a decode step (csrc/peer.cu) ---------------------------
  * Replace the per-hop send of `DistributedModel.forward` (tensorlink/ml/module.py:438-462: tensor -> bytes ->

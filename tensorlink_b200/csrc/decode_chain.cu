@@ -50,6 +50,7 @@ struct ChainParams {
     float* attn_part;               // [M*n_h][cpg][D+2] partial (o, m, l)
     const unsigned char* pf_ptr;
     unsigned long long pf_bytes;
+    unsigned long long* trace;      // optional (tools/trace_chain.py): globaltimer stamps of CTA 0 and the last CTA
     tl_decode_job jobs[DC_MAX_JOBS];
 };
 
@@ -216,14 +217,22 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_chain_kernel(const __gri
         return s_dead == 0;
     };
     int seq = warp;     // this warp's next ring sequence number (advances by NW per stage, only for warp < NW)
+    // optional timeline: [2 CTAs][DC_MAX_JOBS + 1][4] stamps (job start, input staged, work done, dependency passed)
+    const int tr_sel = blockIdx.x == 0 ? 0 : (blockIdx.x == gridDim.x - 1 ? 1 : -1);
+    auto stamp = [&](int j, int k) {
+        if (p.trace && tr_sel >= 0 && tid == 0) p.trace[((size_t)tr_sel * (DC_MAX_JOBS + 1) + j) * 4 + k] = dc_timer();
+    };
+    stamp(DC_MAX_JOBS, 0);
 
     // activations come from the previous kernel: wait for it (no-op without the PDL attribute); the producer warp
     // above streams weights, which nobody writes, without waiting
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    stamp(DC_MAX_JOBS, 1);
 
     for (int j = 0; j < p.n_jobs; ++j) {
         const tl_decode_job& jb = p.jobs[j];
         const bool last_job = j == p.n_jobs - 1;
+        stamp(j, 0);
         if (jb.type == TL_JOB_GEMV) {
             const int N = jb.N, K = jb.K, flags = jb.flags;
             const bf16* x = reinterpret_cast<const bf16*>(jb.x);
@@ -234,22 +243,35 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_chain_kernel(const __gri
             const float eps = jb.eps;
             const int nvec = K >> 3;
             // ---- stage x (possibly written by other CTAs in the previous job: L2-coherent loads), one global pass
+            // (the L2-coherent loads are volatile asm: issued in batches of 4 before anything consumes them, otherwise
+            //  every iteration would pay a full L2 round trip in sequence)
             if (norm_w) {
                 float ss[M];
 #pragma unroll
                 for (int m = 0; m < M; ++m) ss[m] = 0.f;
-                for (int v = tid; v < nvec; v += DC_CT) {
+                constexpr int TB = M == 1 ? 4 : (M == 2 ? 2 : 1);
+                for (int v0 = tid; v0 < nvec; v0 += TB * DC_CT) {
+                    uint4 u[M][TB];
 #pragma unroll
-                    for (int m = 0; m < M; ++m) {
-                        const uint4 u = dc_ldcg_v4(x + (size_t)m * K + (size_t)v * 8);
-                        reinterpret_cast<uint4*>(xs + (size_t)m * K)[v] = u;
-                        const uint32_t* u32 = reinterpret_cast<const uint32_t*>(&u);
+                    for (int m = 0; m < M; ++m)
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float a = bf16_lo(u32[q]), b = bf16_hi(u32[q]);
-                            ss[m] += a * a + b * b;
+                        for (int t = 0; t < TB; ++t)
+                            if (v0 + t * DC_CT < nvec) u[m][t] = dc_ldcg_v4(x + (size_t)m * K + (size_t)(v0 + t * DC_CT) * 8);
+#pragma unroll
+                    for (int m = 0; m < M; ++m)
+#pragma unroll
+                        for (int t = 0; t < TB; ++t) {
+                            const int v = v0 + t * DC_CT;
+                            if (v < nvec) {
+                                reinterpret_cast<uint4*>(xs + (size_t)m * K)[v] = u[m][t];
+                                const uint32_t* u32 = reinterpret_cast<const uint32_t*>(&u[m][t]);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const float a = bf16_lo(u32[q]), b = bf16_hi(u32[q]);
+                                    ss[m] += a * a + b * b;
+                                }
+                            }
                         }
-                    }
                 }
 #pragma unroll
                 for (int m = 0; m < M; ++m) {
@@ -282,23 +304,52 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_chain_kernel(const __gri
                     }
                 }
             } else {
-                for (int v = tid; v < nvec * M; v += DC_CT)
-                    reinterpret_cast<uint4*>(xs)[v] = dc_ldcg_v4(x + (size_t)v * 8);
+                const int tot = nvec * M;
+                for (int v0 = tid; v0 < tot; v0 += 4 * DC_CT) {
+                    uint4 u[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        if (v0 + t * DC_CT < tot) u[t] = dc_ldcg_v4(x + (size_t)(v0 + t * DC_CT) * 8);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        if (v0 + t * DC_CT < tot) reinterpret_cast<uint4*>(xs)[v0 + t * DC_CT] = u[t];
+                }
             }
             dc_bar(1, DC_CT);
+            stamp(j, 1);
 
             const DcGeom g = dc_geom(N, K, NW);
             const bool swiglu = flags & TL_EPI_SWIGLU;
             const int n_out = swiglu ? g.npairs : N;
-            auto finish = [&](int pair, const float (&a0)[M], const float (&a1)[M]) {
+            // bias / residual of a pair are fetched by lane 0 BEFORE the dot product (their L2 round trip would otherwise
+            // sit between the last FMA and the store of every unit)
+            auto preload = [&](int pair, float (&bs)[2], float (&rs)[M][2]) {
+                bs[0] = bs[1] = 0.f;
+#pragma unroll
+                for (int m = 0; m < M; ++m) rs[m][0] = rs[m][1] = 0.f;
+                if (lane != 0) return;
+                const int r0 = 2 * pair;
+                if (flags & TL_EPI_BIAS) {
+                    bs[0] = bf2f(bias[r0]);
+                    bs[1] = bf2f(bias[r0 + 1]);
+                }
+                if (flags & TL_EPI_RESIDUAL) {
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        rs[m][0] = dc_ldcg_bf16(residual + (size_t)m * N + r0);
+                        rs[m][1] = dc_ldcg_bf16(residual + (size_t)m * N + r0 + 1);
+                    }
+                }
+            };
+            auto finish = [&](int pair, const float (&a0)[M], const float (&a1)[M], const float (&bs)[2], const float (&rs)[M][2]) {
                 if (lane != 0) return;
                 const int r0 = 2 * pair;
 #pragma unroll
                 for (int m = 0; m < M; ++m) {
                     float v0 = a0[m], v1 = a1[m];
                     if (flags & TL_EPI_BIAS) {
-                        v0 += bf2f(bias[r0]);
-                        v1 += bf2f(bias[r0 + 1]);
+                        v0 += bs[0];
+                        v1 += bs[1];
                     }
                     if (swiglu) {
                         const float gate = rbf(v0), up = rbf(v1);
@@ -306,8 +357,8 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_chain_kernel(const __gri
                     } else {
                         float t0 = rbf(v0), t1 = rbf(v1);
                         if (flags & TL_EPI_RESIDUAL) {
-                            t0 += dc_ldcg_bf16(residual + (size_t)m * N + r0);
-                            t1 += dc_ldcg_bf16(residual + (size_t)m * N + r0 + 1);
+                            t0 += rs[m][0];
+                            t1 += rs[m][1];
                         }
                         *reinterpret_cast<uint32_t*>(y + (size_t)m * N + r0) = pack_bf16(t0, t1);
                     }
@@ -340,11 +391,14 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_chain_kernel(const __gri
                     const bool valid = unit < g.n_units;
                     const int pair0 = g.p_begin + unit * g.P;
                     float a0[M], a1[M];
+                    float bs[2], rs[M][2];
 #pragma unroll
                     for (int m = 0; m < M; ++m) a0[m] = a1[m] = 0.f;
+                    if (valid && g.chunked) preload(pair0, bs, rs);
                     for (int c = 0; c < g.n_chunks; ++c, seq += NW) {
                         const int stage = seq % n_stages;
                         const uint32_t phase = (uint32_t)(seq / n_stages) & 1u;
+                        if (valid && !g.chunked) preload(pair0, bs, rs);           // first pair of the unit, under the wait
                         mbar_wait(&full_bar[stage], phase);
                         const unsigned char* src = ring + (size_t)stage * DC_STAGE;
                         if (valid) {
@@ -352,13 +406,20 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_chain_kernel(const __gri
                                 const int np = min(g.P, g.p_end - pair0);
                                 for (int pp = 0; pp < np; ++pp) {
                                     float b0[M], b1[M];
+                                    float bn[2], rn[M][2];
 #pragma unroll
                                     for (int m = 0; m < M; ++m) b0[m] = b1[m] = 0.f;
+                                    if (pp + 1 < np) preload(pair0 + pp + 1, bn, rn);   // next pair's, under this pair's FMAs
                                     dot2(reinterpret_cast<const uint4*>(src + (size_t)(2 * pp) * K * 2),
                                          reinterpret_cast<const uint4*>(src + (size_t)(2 * pp + 1) * K * 2), 0, nvec, b0, b1);
 #pragma unroll
                                     for (int m = 0; m < M; ++m) { b0[m] = warp_sum(b0[m]); b1[m] = warp_sum(b1[m]); }
-                                    finish(pair0 + pp, b0, b1);
+                                    finish(pair0 + pp, b0, b1, bs, rs);
+                                    if (pp + 1 < np) {
+                                        bs[0] = bn[0]; bs[1] = bn[1];
+#pragma unroll
+                                        for (int m = 0; m < M; ++m) { rs[m][0] = rn[m][0]; rs[m][1] = rn[m][1]; }
+                                    }
                                 }
                             } else {
                                 const int k0 = c * g.KC;
@@ -372,11 +433,13 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_chain_kernel(const __gri
                     if (valid && g.chunked) {
 #pragma unroll
                         for (int m = 0; m < M; ++m) { a0[m] = warp_sum(a0[m]); a1[m] = warp_sum(a1[m]); }
-                        finish(pair0, a0, a1);
+                        finish(pair0, a0, a1, bs, rs);
                     }
                 }
             }
+            stamp(j, 2);
             if (!last_job && !grid_dep(true, gridDim.x)) break;
+            stamp(j, 3);
         } else if (jb.type == TL_JOB_ATTN) {
             // ---- RoPE (+ q/k norm) + KV append + split-KV attention over all CTAs, one (row, kv head) group at a time
             const int n_h = jb.n_h, n_kv = jb.n_kv, D = jb.d, T_max = jb.T_max;
@@ -607,11 +670,14 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_chain_kernel(const __gri
                 }
             }
             // one arrival per (row, kv head) group, by the CTA that combined it; everybody waits for all groups
+            stamp(j, 2);
             if (!last_job && !grid_dep(s_last != 0, (unsigned)G)) break;
+            stamp(j, 3);
         }
     }
     // ---- self-cleaning: the last CTA to leave resets the counters for the next launch on this sync slot
     dc_bar(1, DC_CT);
+    stamp(DC_MAX_JOBS, 2);
     if (tid == 0) {            // (a producer parked on an empty-slot wait polls s_dead and leaves by itself)
         __threadfence();
         const unsigned prev = atomicAdd(&p.sync[1], 1u);
@@ -625,7 +691,21 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_chain_kernel(const __gri
 
 }  // namespace tl
 
+static unsigned long long* g_chain_trace = nullptr;
+static int g_chain_trace_slots = 0, g_chain_trace_next = 0;
+constexpr int DC_TRACE_WORDS = 2 * (tl::DC_MAX_JOBS + 1) * 4;
+
 extern "C" {
+
+/* debugging aid (tools/trace_chain.py): device buffer of n_slots * 2*(16+1)*4 uint64; every later chain launch takes the
+ * next slot (a captured graph keeps its slots) and stamps it with globaltimer values (CTA 0 and the last CTA, per job:
+ * start / input staged / work done / dependency passed; row 16: kernel entry / previous grid done / exit); NULL = off */
+int tl_decode_chain_trace(void* buf, int n_slots) {
+    g_chain_trace = (unsigned long long*)buf;
+    g_chain_trace_slots = buf ? n_slots : 0;
+    g_chain_trace_next = 0;
+    return TL_OK;
+}
 
 size_t tl_decode_chain_ws(int M, int n_h, int n_kv, int d) {
     // attention partials [M*n_h][cpg][d+2] floats with cpg = CTAs / (n_kv*M) <= 160 / (n_kv*M) on any sm_100 part
@@ -686,6 +766,8 @@ int tl_decode_chain(const tl_decode_job* jobs, int n_jobs, int M, void* sync_slo
     prm.attn_part = (float*)attn_ws;
     prm.pf_ptr = (const unsigned char*)pf_ptr;
     prm.pf_bytes = (((uintptr_t)pf_ptr) & 15) ? 0ull : (unsigned long long)(pf_bytes & ~(size_t)15);
+    prm.trace = (g_chain_trace && g_chain_trace_next < g_chain_trace_slots)
+                    ? g_chain_trace + (size_t)(g_chain_trace_next++) * DC_TRACE_WORDS : nullptr;
     for (int j = 0; j < n_jobs; ++j) prm.jobs[j] = jobs[j];
     const size_t smem = (size_t)n_stages * DC_STAGE + fixed;
     cudaLaunchConfig_t cfg = {};

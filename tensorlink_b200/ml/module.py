@@ -59,8 +59,7 @@ def _config_from_hf(model) -> ShardModelConfig:
 _NEUTRAL_KW = {"use_cache": (True, False, None), "return_dict": (True, None), "output_attentions": (False, None),
                "output_hidden_states": (False, None), "num_beams": (1, None), "num_return_sequences": (1, None),
                "repetition_penalty": (1.0, None), "past_key_values": (None,), "position_ids": (None,),
-               "return_dict_in_generate": (False, None), "temperature": (1.0, None), "top_k": (None, 0, 50),
-               "top_p": (1.0, None), "logits_to_keep": (0, None), "min_new_tokens": (0, None)}
+               "return_dict_in_generate": (False, None), "logits_to_keep": (0, None), "min_new_tokens": (0, None)}
 
 
 def _check_unconsumed(kwargs: dict, what: str):
@@ -319,8 +318,11 @@ class DistributedModel(torch.nn.Module):
     # ------------------------------------------------------------------------------------------ generate
     @torch.no_grad()
     def generate(self, *args, **kwargs) -> Optional[torch.Tensor]:
-        """Greedy generation (module.py:763-769 delegates to HF ``generate``; only ``do_sample=False`` is
-        implemented).  ``input_ids`` [B,S] int64 on the first stage; returns [B,S+new] on every rank.
+        """Generation (module.py:763-769 delegates to HF ``generate``).  Greedy by default; ``do_sample=True`` draws every
+        token on the last stage's GPU from the distribution HF's warpers define — ``temperature`` (default 1.0), ``top_k``
+        (default 50, 0 = off), ``top_p`` (default 1.0) — with a counter-based Philox stream keyed by ``seed`` (extension;
+        default ``torch.initial_seed()``): the same seed reproduces the same tokens (csrc/sample.cu).
+        ``input_ids`` [B,S] int64 on the first stage; returns [B,S+new] on every rank.
         ``streamer``: object with ``put(tensor)`` / ``end()`` (HF BaseStreamer protocol), called on rank 0
         with each new token column, all batch rows (the reference streams row 0 only, worker.py:134-139)."""
         input_ids = kwargs.pop("input_ids", args[0] if args else None)
@@ -328,8 +330,14 @@ class DistributedModel(torch.nn.Module):
         streamer = kwargs.pop("streamer", None)
         use_graph = kwargs.pop("use_graph", True)
         profile = kwargs.pop("profile", False)       # CUDA events around every decode launch -> self.timers["decode_busy_s"]
+        sampling = None
+        temperature, top_k, top_p = kwargs.pop("temperature", None), kwargs.pop("top_k", None), kwargs.pop("top_p", None)
+        seed = kwargs.pop("seed", None)
         if kwargs.pop("do_sample", False):
-            raise NotImplementedError("sampling is not implemented; generate() is greedy (do_sample=False)")
+            sampling = {"temperature": 1.0 if temperature is None else float(temperature), "top_k": 50 if top_k is None else int(top_k),
+                        "top_p": 1.0 if top_p is None else float(top_p), "seed": int(torch.initial_seed() if seed is None else seed)}
+            if sampling["temperature"] <= 0 or not (0 < sampling["top_p"] <= 1) or sampling["top_k"] < 0:
+                raise ValueError(f"invalid sampling parameters {sampling}")
         self._eos = (kwargs.pop("eos_token_id", None), kwargs.pop("pad_token_id", None))
         if self.link.first and input_ids is not None:
             _check_attention_mask(kwargs.pop("attention_mask", None), input_ids.shape)
@@ -337,8 +345,14 @@ class DistributedModel(torch.nn.Module):
             kwargs.pop("attention_mask", None)
         _check_unconsumed(kwargs, "DistributedModel.generate")
         link, st, cfg = self.link, self.stage, self.cfg
-        shape = link.broadcast_object(tuple(input_ids.shape) if link.first else None)
+        shape, sampling = link.broadcast_object((tuple(input_ids.shape), sampling) if link.first else None)
         B, S = shape
+        if hasattr(st, "set_sampling"):
+            st.set_sampling(sampling)               # the last stage draws; greedy (None) restores the argmax path
+            if sampling is not None and st.has_head:
+                st.sample_ctr.zero_()               # a seed names ONE stream: the same call reproduces its tokens
+        elif sampling is not None:
+            raise NotImplementedError("sampling needs the CUDA stage")
         n_mb = min(self.n_pipelines, B)
         if B % n_mb:
             raise ValueError(f"batch {B} not divisible into {n_mb} micro-batches")
@@ -371,10 +385,10 @@ class DistributedModel(torch.nn.Module):
             if not link.last:
                 link.send_next(x.clone())
             elif ring is not None:                         # first token straight into the first stage's mailbox
-                st.head_argmax(x[:, -1, :].contiguous(), ring.first_ids_in[m][:b])
+                st.head_argmax(x[:, -1, :].contiguous(), ring.first_ids_in[m][:b], m)
                 ring.signal_ids(m)
             else:
-                st.head_argmax(x[:, -1, :].contiguous(), st.ids_dec[m][:b])
+                st.head_argmax(x[:, -1, :].contiguous(), st.ids_dec[m][:b], m)
                 if multi:
                     link.send_up(st.ids_dec[m][:b].clone(), 0)
         if ring is not None:

@@ -46,6 +46,9 @@ class CudaStage:
                                        dtype=torch.uint8, device=dev)
             self.logits_dec = torch.empty(max_batch, cfg.vocab, dtype=torch.bfloat16, device=dev)
             self.hn = torch.empty(max_batch, cfg.hidden, dtype=torch.bfloat16, device=dev)
+            self.sampling: Optional[dict] = None        # set by generate(do_sample=True): temperature / top_k / top_p / seed
+            self.sample_ctr = torch.zeros(n_slots, max_batch, dtype=torch.int32, device=dev)
+            self.sample_ws: Optional[torch.Tensor] = None
 
     # ------------------------------------------------------------------------------------------ pieces
     def embed(self, ids: torch.Tensor) -> torch.Tensor:
@@ -64,8 +67,27 @@ class CudaStage:
         hn = nat.rmsnorm_fwd(hidden.contiguous(), v["norm"], cfg.rms_eps)
         return nat.gemm(hn, v["head"])
 
-    def head_argmax(self, hidden: torch.Tensor, ids_out: torch.Tensor):
-        """greedy next token for [B,H] rows -> ids_out [B] int64 (bit-exact target: torch.argmax of bf16 logits)."""
+    def set_sampling(self, sampling: Optional[dict]):
+        """None = greedy.  Changing the mode drops the captured decode graphs (the launch sequence differs)."""
+        if not self.has_head or sampling == self.sampling:
+            return
+        self.sampling = sampling
+        self.graphs.clear()
+        self.sample_ctr.zero_()
+        if sampling is not None and self.sample_ws is None:
+            self.sample_ws = torch.empty(nat.sample_ws(self.max_batch), dtype=torch.uint8, device=self.device)
+
+    def head_argmax(self, hidden: torch.Tensor, ids_out: torch.Tensor, slot: int = 0):
+        """next token for [B,H] rows -> ids_out [B] int64: greedy (bit-exact target: torch.argmax of bf16 logits) or, after
+        ``set_sampling``, one draw per row from the warped distribution (csrc/sample.cu)."""
+        self._head_greedy(hidden, ids_out)
+        if self.sampling is not None:
+            B = hidden.shape[0]
+            s = self.sampling
+            nat.sample(self.logits_dec[:B], ids_out, self.sample_ctr[slot], self.sample_ws, s["temperature"], s["top_k"], s["top_p"],
+                       s["seed"] + 0x9E3779B97F4A7C15 * slot)
+
+    def _head_greedy(self, hidden: torch.Tensor, ids_out: torch.Tensor):
         cfg, v = self.cfg, self.params.v
         B = hidden.shape[0]
         if B <= gemv_max_rows():
@@ -90,7 +112,7 @@ class CudaStage:
             x = ring.x_in[slot][:B]
         if self.has_head:
             grp.decode_step_inplace(x, advance=False)
-            self.head_argmax(x, ring.first_ids_in[slot][:B])
+            self.head_argmax(x, ring.first_ids_in[slot][:B], slot)
             ring.signal_ids(slot, bump=grp.pos_dev)              # the closing signal also advances the cache position
         else:
             grp.decode_step_inplace(x, out=ring.next_x_in[slot][:B], advance=False)
@@ -105,7 +127,7 @@ class CudaStage:
             nat.embed_fwd(self.ids_dec[slot][:B], self.params.v["embed"], out=x)
         self.slots[slot].decode_step_inplace(x)
         if self.has_head:
-            self.head_argmax(x, self.ids_dec[slot][:B])
+            self.head_argmax(x, self.ids_dec[slot][:B], slot)
 
     def decode(self, slot: int, B: int, use_graph: bool = True, ring=None):
         """One token for slot's rows: [embed ->] layers [-> norm + lm_head + argmax], as ONE graph launch.

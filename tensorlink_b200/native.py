@@ -49,6 +49,7 @@ _SIGS = {
                                    c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "tl_attn_decode_fused": (c_int, [c_void_p] * 9 + [c_float, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "tl_decode_chain_ws": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "tl_decode_chain_trace": (c_int, [c_void_p, c_int]),
     "tl_decode_chain": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
     "tl_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),
     "tl_peer_open": (c_int, [c_void_p, POINTER(c_void_p)]),
@@ -61,6 +62,9 @@ _SIGS = {
     "tl_lmhead_argmax": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_size_t,
                                  c_int, c_int, c_int, c_void_p]),
     "tl_argmax_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
+    "tl_sample_ws": (c_size_t, [c_int]),
+    "tl_sample": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_float, ctypes.c_uint64, c_void_p, c_void_p, c_size_t,
+                          c_void_p]),
     "tl_advance_pos": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "tl_append_token": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "tl_swiglu_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
@@ -325,6 +329,20 @@ def argmax_bf16(logits, ids_out, ws):
            "tl_argmax_bf16")
 
 
+def sample_ws(M: int) -> int:
+    return int(load().tl_sample_ws(M))
+
+
+def sample(logits, ids_out, counters, ws, temperature: float = 1.0, top_k: int = 0, top_p: float = 1.0, seed: int = 0):
+    """ids_out[m] ~ softmax(top-p(top-k(logits[m] / temperature))); ``counters`` int32[M] advance by one per call."""
+    require_device()
+    _bf16(logits)
+    M, V = logits.shape
+    assert ids_out.dtype == torch.int64 and counters.dtype == torch.int32 and counters.numel() >= M
+    _check(load().tl_sample(_p(logits), _p(ids_out), M, V, float(temperature), int(top_k or 0), float(top_p), int(seed) & (2 ** 64 - 1),
+                            _p(counters), _p(ws), ws.numel() * ws.element_size(), _stream()), "tl_sample")
+
+
 def advance_pos(pos_dev, kv_len_dev, delta: int):
     require_device()
     _check(load().tl_advance_pos(_p(pos_dev), _p(kv_len_dev), delta, _stream()), "tl_advance_pos")
@@ -487,6 +505,14 @@ def attn_decode_fused(qkv, k_cache, v_cache, out, pos_dev, cos_tab, sin_tab, q_n
 
 def decode_chain_ws(M: int, n_h: int, n_kv: int, d: int) -> int:
     return int(load().tl_decode_chain_ws(M, n_h, n_kv, d))
+
+
+CHAIN_TRACE_WORDS = 2 * (CHAIN_MAX_JOBS + 1) * 4
+
+
+def decode_chain_trace(buf: Optional[torch.Tensor]):
+    """``buf``: int64 [n_slots, CHAIN_TRACE_WORDS] (or None to switch tracing off)."""
+    _check(load().tl_decode_chain_trace(_p(buf), 0 if buf is None else buf.shape[0]), "tl_decode_chain_trace")
 
 
 def make_job(type_, **kw) -> DecodeJob:

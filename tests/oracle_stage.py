@@ -64,7 +64,7 @@ class OracleStage:
         with torch.no_grad():
             return F.linear(O.rmsnorm(hidden, self.sd["model.norm.weight"], self.cfg.rms_eps), self.sd["lm_head.weight"])
 
-    def head_argmax(self, hidden, ids_out):
+    def head_argmax(self, hidden, ids_out, slot=0):
         ids_out.copy_(self.head_logits(hidden).float().argmax(-1))
 
     def decode(self, slot, B, use_graph=True):

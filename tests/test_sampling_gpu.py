@@ -1,0 +1,113 @@
+"""Device-side sampling (csrc/sample.cu) against the distribution HF's warpers + ``torch.multinomial`` define on the same
+bf16 logits.  ``torch.multinomial`` consumes its generator differently, so ids cannot match draw for draw; what is pinned:
+the SUPPORT (every drawn id lies in the set HF's TemperatureLogitsWarper -> TopKLogitsWarper -> TopPLogitsWarper keep, and
+every kept id with non-negligible mass is reachable), the FREQUENCIES (chi-square against the exact warped softmax), and
+determinism (a seed reproduces its tokens; the device counter gives a fresh draw per call / graph replay)."""
+import pytest
+import torch
+
+from tensorlink_b200.ml import configs as C
+from tensorlink_b200.ml.weights import synthetic_tokens
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def nat():
+    from tensorlink_b200 import native
+    native.require_device()
+    return native
+
+
+def hf_warped_probs(logits_bf16, temperature, top_k, top_p):
+    """The distribution HF samples from (transformers LogitsProcessor semantics), fp32 on the CPU."""
+    from transformers.generation.logits_process import TemperatureLogitsWarper, TopKLogitsWarper, TopPLogitsWarper
+    s = logits_bf16.float().clone()
+    if temperature != 1.0:
+        s = TemperatureLogitsWarper(temperature)(None, s)
+    if top_k:
+        s = TopKLogitsWarper(top_k)(None, s)
+    if top_p < 1.0:
+        s = TopPLogitsWarper(top_p)(None, s)
+    return torch.softmax(s, -1)
+
+
+def draw(nat, logits, n, **kw):
+    M, V = logits.shape
+    ids = torch.empty(M, dtype=torch.int64, device="cuda")
+    ctr = torch.zeros(M, dtype=torch.int32, device="cuda")
+    ws = torch.empty(nat.sample_ws(M), dtype=torch.uint8, device="cuda")
+    lg = logits.cuda()
+    out = []
+    for _ in range(n):
+        nat.sample(lg, ids, ctr, ws, **kw)
+        out.append(ids.clone())
+    assert ctr.cpu().tolist() == [n] * M
+    return torch.stack(out, 1).cpu()                       # [M, n]
+
+
+@pytest.mark.parametrize("temperature,top_k,top_p", [(1.0, 0, 1.0), (0.7, 0, 1.0), (1.0, 5, 1.0), (1.3, 0, 0.6), (0.8, 12, 0.9)])
+def test_frequencies_match_the_warped_softmax(nat, temperature, top_k, top_p):
+    g = torch.Generator().manual_seed(5)
+    V, n = 48, 20000
+    logits = (torch.randn(2, V, generator=g) * 2.0).bfloat16()
+    probs = hf_warped_probs(logits, temperature, top_k, top_p)
+    ids = draw(nat, logits, n, temperature=temperature, top_k=top_k, top_p=top_p, seed=1234)
+    for m in range(2):
+        counts = torch.bincount(ids[m], minlength=V).double()
+        kept = probs[m] > 0
+        assert counts[~kept].sum() == 0, "a token outside HF's kept set was drawn"
+        exp = probs[m].double() * n
+        big = exp >= 5
+        chi2 = float((((counts - exp) ** 2) / exp.clamp_min(1e-12))[big].sum())
+        dof = int(big.sum()) - 1
+        assert chi2 < dof + 6 * (2 * dof) ** 0.5 + 10, (chi2, dof)       # ~6 sigma of the chi-square distribution
+
+
+def test_full_vocabulary_support_and_ties(nat):
+    """V = 151,936 bf16 logits (many exact ties): top-k keeps every logit >= the k-th largest like HF; top-p never leaves
+    HF's kept set."""
+    g = torch.Generator().manual_seed(6)
+    V = 151936
+    logits = (torch.randn(1, V, generator=g) * 1.5).bfloat16()
+    for kw in (dict(temperature=1.0, top_k=50, top_p=1.0), dict(temperature=0.9, top_k=0, top_p=0.8), dict(temperature=1.0, top_k=200, top_p=0.95)):
+        probs = hf_warped_probs(logits, kw["temperature"], kw["top_k"], kw["top_p"])[0]
+        ids = draw(nat, logits, 400, seed=9, **kw)[0]
+        assert bool((probs[ids] > 0).all()), kw
+        assert len(set(ids.tolist())) > 5
+    one = draw(nat, logits, 8, temperature=1.0, top_k=1, top_p=1.0, seed=3)[0]
+    top = logits[0].float()
+    assert all(float(top[i]) == float(top.max()) for i in one.tolist())       # top_k = 1: an argmax (any tied maximum)
+
+
+def test_seed_reproduces_and_counter_advances(nat):
+    g = torch.Generator().manual_seed(7)
+    logits = (torch.randn(3, 1000, generator=g) * 2.0).bfloat16()
+    a = draw(nat, logits, 32, temperature=1.0, top_k=0, top_p=1.0, seed=42)
+    b = draw(nat, logits, 32, temperature=1.0, top_k=0, top_p=1.0, seed=42)
+    c = draw(nat, logits, 32, temperature=1.0, top_k=0, top_p=1.0, seed=43)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    assert len(set(a[0].tolist())) > 8                     # the counter advances: not the same draw 32 times
+    assert not torch.equal(a[0], a[1])                     # rows use different streams
+
+
+def test_generate_do_sample_end_to_end():
+    """``generate(do_sample=True, ...)`` through the captured decode graph: reproducible per seed, different across seeds,
+    every sampled token inside HF's kept set for the logits of its own prefix (teacher-forced check), greedy unaffected."""
+    from tensorlink_b200.ml import DistributedModel
+    cfg = C.TINY_QWEN2_D128
+    ids = synthetic_tokens(cfg, 2, 12)
+    dm = DistributedModel(cfg, training=False, max_batch=2, max_seq=64)
+    greedy = dm.generate(ids, max_new_tokens=16).cpu()
+    kw = dict(do_sample=True, temperature=0.9, top_k=20, top_p=0.95, max_new_tokens=16)
+    a = dm.generate(ids, seed=11, **kw).cpu()
+    b = dm.generate(ids, seed=11, **kw).cpu()
+    c = dm.generate(ids, seed=12, **kw).cpu()
+    assert torch.equal(a, b) and not torch.equal(a, c) and not torch.equal(a, greedy)
+    assert torch.equal(dm.generate(ids, max_new_tokens=16).cpu(), greedy)           # back to greedy: same ids as before
+    logits = dm(a[:, :-1]).logits.cpu()                                             # logits of every prefix of the sampled text
+    for r in range(2):
+        for s in range(16):
+            # (prefill and decode logits differ in the last bf16 bit: a slightly wider set absorbs boundary flips)
+            p = hf_warped_probs(logits[r:r + 1, 11 + s], 0.9, 24, 0.97)[0]
+            assert float(p[a[r, 12 + s]]) > 0, (r, s)
