@@ -44,6 +44,57 @@ def payloads():
     }
 
 
+def reference_packets(frames):
+    """FORWARD / BACKWARD packets built by the reference's own ``Torchnode.send_forward`` / ``send_backward``
+    (p2p/torch_node.py:825-836, :865-869) and parsed back by its ``_handle_forward`` / ``_handle_backward`` (:251-299,
+    :225-249), run as unbound functions on a recorder object (a real Torchnode needs sockets and RSA keys)."""
+    import json
+    import sys
+    from oracle.ref_shim import REFERENCE_ROOT
+    sys.path.insert(0, REFERENCE_ROOT)
+    try:
+        import tensorlink.p2p.torch_node as TN
+    finally:
+        sys.path.remove(REFERENCE_ROOT)
+    mid = "ab" * 32
+
+    class Rec:
+        VERBOSE = 0
+        role = "W"
+
+        def __init__(self):
+            self.sent, self.stored, self.nodes, self.modules = [], [], {"peer": None}, {mid: {"forward_queue": {}}}
+            self.memory_manager = {}
+
+        def send_to_node(self, node, data):
+            self.sent.append(data)
+
+        def debug_print(self, *a, **k):
+            pass
+
+        def _store_tensor_in_shared_memory(self, key, tensor, backward=False):
+            self.stored.append((key, len(tensor), backward))
+
+    class Peer:
+        node_id, ghosts = "peer", 0
+
+    rec, key = Rec(), [5, 1, mid]
+    fwd_payload = len(frames["nested"]).to_bytes(8, "big") + frames["nested"] + frames["live_ins"]
+    TN.Torchnode.send_forward(rec, None, fwd_payload, key, mid)
+    TN.Torchnode.send_backward(rec, None, frames["decode_row"], key)
+    fwd_packet, bwd_packet = rec.sent
+    # the reference's own parsers on those packets
+    eos = fwd_packet.find(b"::")
+    size = int(fwd_packet[7:eos])
+    tail = json.loads(fwd_packet[eos + 2 + size:])
+    assert TN.Torchnode._handle_backward(rec, bwd_packet, Peer()) is True
+    (bkey, bsize, bflag), = rec.stored
+    return {"module_id": mid, "key": key, "forward_payload": fwd_payload, "backward_payload": frames["decode_row"],
+            "forward_packet": fwd_packet, "backward_packet": bwd_packet,
+            "ref_parsed_forward": {"size": size, "module_id": tail["module_id"], "key": tail["key"]},
+            "ref_parsed_backward": {"size": bsize, "key": list(bkey)}}
+
+
 def main():
     _, utils = import_reference()
     items = payloads()
@@ -56,7 +107,8 @@ def main():
     frames_cache = utils.tensor_to_bytes(cd)
     pkv = cd["past_key_values"]                       # stored as plain lists; the tests rebuild the stand-in object
     cd["past_key_values"] = {"__dynamic_cache__": True, "key_cache": pkv.key_cache, "value_cache": pkv.value_cache}
-    torch.save({"payloads": items, "frames": frames, "cached_decode": {"payload": cd, "frame": frames_cache}}, OUT)
+    torch.save({"payloads": items, "frames": frames, "cached_decode": {"payload": cd, "frame": frames_cache},
+                "packets": reference_packets(frames)}, OUT)
     print("wrote", OUT, {k: len(v) for k, v in frames.items()})
 
 

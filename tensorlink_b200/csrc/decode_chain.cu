@@ -15,10 +15,15 @@
 // * A dependency is one counter in global memory: writers publish with red.release.gpu, every CTA's thread 0 polls
 //   with ld.acquire.gpu.  No cooperative-groups grid sync, no per-thread fences.  Every spin gives up after 2 s and
 //   raises an error word instead of hanging the GPU.
+// * Units of a GEMV job (one ring stage of consecutive weight rows) are handed out in groups by a ticket counter, not
+//   split statically: an SM that streams faster takes more groups, so all CTAs finish a job within one group of each
+//   other and the dependency wait behind it stays shorter than what the ring bridges.
 // * The attention job is split-KV over ALL CTAs, once per kv head (GQA: the n_rep query heads that share a kv head are
 //   handled together, so every cached key / value byte is read exactly once chip-wide): CTA = (row, kv head, key
-//   range) -> partial (m, l, o) per query head -> the last CTA of a (row, kv head) group to arrive combines the
-//   partials and publishes the group; RoPE, the Qwen3 q/k norm and the KV append are fused in.
+//   range); inside it warp r owns query head r end to end over 32-key tiles staged in shared memory (scores with
+//   lane = key, online softmax in registers, P.V with lane = output dims; the tile's global loads fly under the q
+//   round trip) -> partial (m, l, o) per query head -> the last CTA of a group to arrive combines the partials and
+//   publishes the group; RoPE, the Qwen3 q/k norm and the KV append are fused in.
 // * Job descriptors travel in kernel parameter space (constant bank): no global-memory fetch at a job boundary.
 // * Programmatic dependent launch on both sides; after its last load the producer queues L2 prefetches of the next
 //   launch's first weights.
@@ -34,20 +39,25 @@ namespace tl {
 constexpr int DC_CW = 8;                       // consumer warps
 constexpr int DC_CT = DC_CW * 32;              // consumer threads
 constexpr int DC_THREADS = DC_CT + 32;         // + producer warp
-constexpr int DC_STAGE = 16 * 1024;
-constexpr int DC_KC = 4096;
-constexpr int DC_MAX_STAGES = 16;
+constexpr int DC_MAX_STAGES = 24;
 constexpr int DC_MAX_JOBS = 16;
 constexpr int DC_MAX_M = 4;
-constexpr int DC_MIN_KEYS = 32;                // an attention CTA takes at least this many keys
-constexpr int DC_ATTN_FIXED = 8 * 128 + 128 + 128 + 8 * 128 + 64 + 16;   // floats: sq, sk, sv, so, sred, sml
+constexpr int DC_TILE = 32;                    // keys per attention tile (an attention CTA takes whole tiles)
+constexpr int DC_KT_MAX = 128 * 2 + 16;        // bytes per K / V tile row at d = 128 (16 bytes of padding: conflict-free rows)
+// shared memory of the attention job: sq[8][128] f32 | sk[128] sv[128] f32 | sp[8][32] f32 | K tile | V tile
+constexpr int DC_ATTN_BYTES = 8 * 128 * 4 + 2 * 128 * 4 + 8 * DC_TILE * 4 + 2 * DC_TILE * DC_KT_MAX;
+constexpr int DC_GB = 8;                       // ring of unit-group tickets (> n_stages / NW + 1: the producer's lead in groups)
+constexpr int DC_JOBCTR = 64;                  // word offset of the per-job unit counters inside a sync slot
+constexpr int DC_STAT_OFF = 2 * (DC_MAX_JOBS + 1) * 4 + DC_MAX_JOBS * 160;   // trace: per-job wait / busy cycle counters
 constexpr unsigned long long DC_TIMEOUT_NS = 2000000000ull;
 
 struct ChainParams {
     int n_jobs, n_stages, NW, xs_bytes;
-    int chunk_cap, pad0;
-    unsigned* sync;                 // [0] barrier counter, [1] exit counter, [2] error word, [4..] group counters
-    float* attn_part;               // [M*n_h][cpg][D+2] partial (o, m, l)
+    int dynamic, stage_bytes;       // dynamic: units are handed out by tickets (1) or split statically per CTA (0)
+    int kc, l2_ahead;               // stage_bytes: one ring slot; kc: K chunk (elements) of a row pair that exceeds a slot;
+                                    // l2_ahead: bytes per CTA the L2 prefetch cursor may lead the shared-memory loads by
+    unsigned* sync;                 // [0] barrier, [1] exit, [2] error, [4..] attention group counters, [64..] unit tickets
+    float* attn_part;               // [M*n_h][cpg][D+4] partial (o[D], m, l, pad, pad)
     const unsigned char* pf_ptr;
     unsigned long long pf_bytes;
     unsigned long long* trace;      // optional (tools/trace_chain.py): globaltimer stamps of CTA 0 and the last CTA
@@ -87,19 +97,22 @@ __device__ __forceinline__ bool dc_mbar_wait(uint64_t* bar, uint32_t parity, vol
     return true;
 }
 
+// A unit = P consecutive row pairs (one ring stage when a pair fits) or one pair in n_chunks K-chunks (one stage each).
+// Units are numbered over the whole matrix.  Static mode: CTA c owns the contiguous units [u_begin, u_end).  Dynamic mode:
+// groups of NW consecutive units are handed out by a ticket counter, so a faster SM simply takes more groups and every
+// CTA finishes a job within one group of the others.
 struct DcGeom {
-    int npairs, p_begin, p_end, P, n_units, n_groups, KC, n_chunks;
+    int npairs, P, U, u_begin, u_end, KC, n_chunks;
     bool chunked;
 };
-__device__ __forceinline__ DcGeom dc_geom(int N, int K, int NW) {
+__device__ __forceinline__ DcGeom dc_geom(int N, int K, int DC_STAGE, int DC_KC) {
     DcGeom g;
     g.npairs = N >> 1;
-    g.p_begin = (int)((long long)blockIdx.x * g.npairs / gridDim.x);
-    g.p_end = (int)((long long)(blockIdx.x + 1) * g.npairs / gridDim.x);
-    g.chunked = K > DC_KC || (size_t)K * 4 > DC_STAGE;
+    g.chunked = K > DC_KC || (size_t)K * 4 > (size_t)DC_STAGE;
     g.P = g.chunked ? 1 : min(8, (int)(DC_STAGE / ((size_t)K * 4)));
-    g.n_units = (g.p_end - g.p_begin + g.P - 1) / g.P;
-    g.n_groups = (g.n_units + NW - 1) / NW;
+    g.U = (g.npairs + g.P - 1) / g.P;
+    g.u_begin = (int)((long long)blockIdx.x * g.U / gridDim.x);
+    g.u_end = (int)((long long)(blockIdx.x + 1) * g.U / gridDim.x);
     g.KC = g.chunked ? DC_KC : K;
     g.n_chunks = (K + g.KC - 1) / g.KC;
     return g;
@@ -108,14 +121,15 @@ __device__ __forceinline__ DcGeom dc_geom(int N, int K, int NW) {
 template <int M>
 __global__ void __launch_bounds__(DC_THREADS, 1) decode_chain_kernel(const __grid_constant__ ChainParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int n_stages = p.n_stages, NW = p.NW;
+    const int n_stages = p.n_stages, NW = p.NW, DC_STAGE = p.stage_bytes, DC_KC = p.kc;
     unsigned char* ring = smem;
     bf16* xs = reinterpret_cast<bf16*>(smem + (size_t)n_stages * DC_STAGE);                       // [M][K_max]
-    float* attn_s = reinterpret_cast<float*>(smem + (size_t)n_stages * DC_STAGE + (size_t)p.xs_bytes);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(attn_s + DC_ATTN_FIXED + (size_t)8 * p.chunk_cap);
+    unsigned char* attn_s = smem + (size_t)n_stages * DC_STAGE + (size_t)p.xs_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(attn_s + DC_ATTN_BYTES);
     uint64_t* empty_bar = full_bar + DC_MAX_STAGES;
     __shared__ float s_part[DC_CW][M];
     __shared__ int s_dead, s_last;
+    __shared__ int s_gbase[DC_GB];            // first unit of the unit groups in flight (written by the producer)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
@@ -135,40 +149,100 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_chain_kernel(const __gri
     if (warp == DC_CW) {
         // ================================================================= producer: weights of every GEMV job, in order
         if (lane == 0) {
-            int stage = 0;
+            int stage = 0, gseq = 0;
             uint32_t phase = 0;
             bool alive = true;
-            for (int j = 0; j < p.n_jobs && alive; ++j) {
+            unsigned* const tickets = p.sync + DC_JOBCTR;
+            // Second-level ring (static split only): an L2 prefetch cursor runs over this CTA's weight ranges of all jobs,
+            // up to l2_ahead bytes in front of the shared-memory loads.  When the ring is full (consumers are crossing a
+            // dependency) the producer keeps HBM streaming into L2; afterwards the ring refills at L2 speed.
+            long long loaded = 0, prefetched = 0;
+            int pf_job = 0;
+            long long pf_off = 0;
+            auto pf_range = [&](int j, const unsigned char*& base, long long& len) {
+                const tl_decode_job& q = p.jobs[j];
+                const DcGeom h = dc_geom(q.N, q.K, DC_STAGE, DC_KC);
+                const long long r0 = (long long)h.u_begin * h.P * 2, r1 = min((long long)h.u_end * h.P * 2, (long long)q.N);
+                base = reinterpret_cast<const unsigned char*>(q.W) + r0 * q.K * 2;
+                len = (r1 - r0) * q.K * 2;
+            };
+            auto pump = [&](int max_issue) {
+                if (p.dynamic || p.l2_ahead <= 0) return;
+                while (max_issue-- > 0 && pf_job < p.n_jobs && prefetched < loaded + p.l2_ahead) {
+                    if (p.jobs[pf_job].type != TL_JOB_GEMV) { ++pf_job; pf_off = 0; continue; }
+                    const unsigned char* base;
+                    long long len;
+                    pf_range(pf_job, base, len);
+                    if (pf_off >= len) { ++pf_job; pf_off = 0; continue; }
+                    const uint32_t sz = (uint32_t)min(16384ll, len - pf_off);
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + pf_off), "r"(sz & ~15u) : "memory");
+                    pf_off += sz;
+                    prefetched += sz;
+                }
+            };
+            // the first ticket of a job is requested one job ahead: its round trip never stalls the stream
+            int first_ticket = 0;
+            int jn = 0;
+            while (jn < p.n_jobs && p.jobs[jn].type != TL_JOB_GEMV) ++jn;
+            if (p.dynamic && jn < p.n_jobs) first_ticket = (int)atomicAdd(&tickets[jn], (unsigned)NW);
+            for (int j = jn; j < p.n_jobs && alive; j = jn) {
                 const tl_decode_job& jb = p.jobs[j];
-                if (jb.type != TL_JOB_GEMV) continue;
-                const DcGeom g = dc_geom(jb.N, jb.K, NW);
+                jn = j + 1;
+                while (jn < p.n_jobs && p.jobs[jn].type != TL_JOB_GEMV) ++jn;
+                const DcGeom g = dc_geom(jb.N, jb.K, DC_STAGE, DC_KC);
                 const bf16* W = reinterpret_cast<const bf16*>(jb.W);
                 const int K = jb.K;
-                for (int gi = 0; gi < g.n_groups && alive; ++gi)
-                    for (int c = 0; c < g.n_chunks && alive; ++c)
+                int base = p.dynamic ? first_ticket : g.u_begin;
+                const int u_end = p.dynamic ? g.U : g.u_end;
+                long long pwait = 0;
+                if (p.dynamic && jn < p.n_jobs) first_ticket = (int)atomicAdd(&tickets[jn], (unsigned)NW);
+                for (;;) {
+                    const bool term = base >= u_end;                 // terminator group: NW empty stages, consumers leave the job
+                    int next = base + NW;
+                    if (p.dynamic && !term) next = (int)atomicAdd(&tickets[j], (unsigned)NW);   // used one group later
+                    const int n_c = term ? 1 : g.n_chunks;
+                    for (int c = 0; c < n_c && alive; ++c)
                         for (int w = 0; w < NW; ++w) {
-                            const int unit = gi * NW + w;
-                            if (!dc_mbar_wait(&empty_bar[stage], phase ^ 1, &s_dead)) { alive = false; break; }
+                            const int unit = base + w;
+                            const long long tw0 = clock64();
+                            pump(2);
+                            {
+                                int it = 0;
+                                while (!mbar_try_wait(&empty_bar[stage], phase ^ 1)) {      // ring full: keep HBM busy through L2
+                                    pump(1);
+                                    if (((++it) & 0xfff) == 0 && s_dead) { alive = false; break; }
+                                }
+                                if (!alive) break;
+                            }
+                            pwait += clock64() - tw0;
+                            if (c == 0 && w == 0) s_gbase[gseq & (DC_GB - 1)] = term ? -1 : base;   // (released by the arrive below)
                             unsigned char* dst = ring + (size_t)stage * DC_STAGE;
-                            if (unit >= g.n_units) {
+                            if (term || unit >= u_end) {
                                 mbar_expect_tx(&full_bar[stage], 0);
                             } else {
-                                const int pair0 = g.p_begin + unit * g.P;
-                                const int np = min(g.P, g.p_end - pair0);
+                                const int pair0 = unit * g.P;
+                                const int np = min(g.P, g.npairs - pair0);
                                 if (!g.chunked) {
                                     const uint32_t bytes = (uint32_t)(2 * np) * (uint32_t)K * 2u;
                                     mbar_expect_tx(&full_bar[stage], bytes);
                                     bulk_load_1d(dst, W + (size_t)(2 * pair0) * K, bytes, &full_bar[stage]);
+                                    loaded += bytes;
                                 } else {
                                     const int k0 = c * g.KC;
                                     const uint32_t bytes = (uint32_t)min(g.KC, K - k0) * 2u;
                                     mbar_expect_tx(&full_bar[stage], 2 * bytes);
                                     bulk_load_1d(dst, W + (size_t)(2 * pair0) * K + k0, bytes, &full_bar[stage]);
                                     bulk_load_1d(dst + (size_t)g.KC * 2, W + (size_t)(2 * pair0 + 1) * K + k0, bytes, &full_bar[stage]);
+                                    loaded += 2 * bytes;
                                 }
                             }
                             if (++stage == n_stages) { stage = 0; phase ^= 1; }
                         }
+                    ++gseq;
+                    if (term || !alive) break;
+                    base = next;
+                }
+                if (p.trace && blockIdx.x == 0) p.trace[DC_STAT_OFF + (size_t)j * 4 + 2] = (unsigned long long)pwait;
             }
             // every load of this CTA is issued: queue L2 prefetches of this CTA's slice of the NEXT launch's first weights
             if (alive && p.pf_bytes) {
@@ -217,10 +291,14 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_chain_kernel(const __gri
         return s_dead == 0;
     };
     int seq = warp;     // this warp's next ring sequence number (advances by NW per stage, only for warp < NW)
+    int gseq = 0;       // unit groups seen so far (index into the ticket ring s_gbase)
     // optional timeline: [2 CTAs][DC_MAX_JOBS + 1][4] stamps (job start, input staged, work done, dependency passed)
     const int tr_sel = blockIdx.x == 0 ? 0 : (blockIdx.x == gridDim.x - 1 ? 1 : -1);
     auto stamp = [&](int j, int k) {
-        if (p.trace && tr_sel >= 0 && tid == 0) p.trace[((size_t)tr_sel * (DC_MAX_JOBS + 1) + j) * 4 + k] = dc_timer();
+        if (!p.trace || tid != 0) return;
+        const unsigned long long now = dc_timer();
+        if (tr_sel >= 0) p.trace[((size_t)tr_sel * (DC_MAX_JOBS + 1) + j) * 4 + k] = now;
+        if (k == 2 && j < DC_MAX_JOBS) p.trace[2 * (DC_MAX_JOBS + 1) * 4 + (size_t)j * 160 + blockIdx.x] = now;   // every CTA: work done
     };
     stamp(DC_MAX_JOBS, 0);
 
@@ -318,7 +396,8 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_chain_kernel(const __gri
             dc_bar(1, DC_CT);
             stamp(j, 1);
 
-            const DcGeom g = dc_geom(N, K, NW);
+            const DcGeom g = dc_geom(N, K, DC_STAGE, DC_KC);
+            const int u_end = p.dynamic ? g.U : g.u_end;
             const bool swiglu = flags & TL_EPI_SWIGLU;
             const int n_out = swiglu ? g.npairs : N;
             // bias / residual of a pair are fetched by lane 0 BEFORE the dot product (their L2 round trip would otherwise
@@ -385,25 +464,43 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_chain_kernel(const __gri
                     }
                 }
             };
+            long long cwait = 0;
+            const long long cjob0 = clock64();
             if (warp < NW) {
-                for (int gi = 0; gi < g.n_groups; ++gi) {
-                    const int unit = gi * NW + warp;
-                    const bool valid = unit < g.n_units;
-                    const int pair0 = g.p_begin + unit * g.P;
+                for (;;) {                                   // unit groups until the producer's terminator group
+                    int stage = seq % n_stages;
+                    uint32_t phase = (uint32_t)(seq / n_stages) & 1u;
+                    long long tw0 = clock64();
+                    mbar_wait(&full_bar[stage], phase);
+                    cwait += clock64() - tw0;
+                    const int base = s_gbase[gseq & (DC_GB - 1)];
+                    ++gseq;
+                    if (base < 0) {                          // terminator: one empty stage per warp
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+                        seq += NW;
+                        break;
+                    }
+                    const int unit = base + warp;
+                    const bool valid = unit < u_end;
+                    const int pair0 = unit * g.P;
                     float a0[M], a1[M];
                     float bs[2], rs[M][2];
 #pragma unroll
                     for (int m = 0; m < M; ++m) a0[m] = a1[m] = 0.f;
-                    if (valid && g.chunked) preload(pair0, bs, rs);
+                    if (valid) preload(pair0, bs, rs);
                     for (int c = 0; c < g.n_chunks; ++c, seq += NW) {
-                        const int stage = seq % n_stages;
-                        const uint32_t phase = (uint32_t)(seq / n_stages) & 1u;
-                        if (valid && !g.chunked) preload(pair0, bs, rs);           // first pair of the unit, under the wait
-                        mbar_wait(&full_bar[stage], phase);
+                        if (c) {
+                            stage = seq % n_stages;
+                            phase = (uint32_t)(seq / n_stages) & 1u;
+                            tw0 = clock64();
+                            mbar_wait(&full_bar[stage], phase);
+                            cwait += clock64() - tw0;
+                        }
                         const unsigned char* src = ring + (size_t)stage * DC_STAGE;
                         if (valid) {
                             if (!g.chunked) {
-                                const int np = min(g.P, g.p_end - pair0);
+                                const int np = min(g.P, g.npairs - pair0);
                                 for (int pp = 0; pp < np; ++pp) {
                                     float b0[M], b1[M];
                                     float bn[2], rn[M][2];
@@ -437,13 +534,20 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_chain_kernel(const __gri
                     }
                 }
             }
+            if (p.trace && blockIdx.x == 0 && tid == 0) {       // warp 0: cycles waiting for weights vs total cycles in the job's loop
+                p.trace[DC_STAT_OFF + (size_t)j * 4 + 0] = (unsigned long long)cwait;
+                p.trace[DC_STAT_OFF + (size_t)j * 4 + 1] = (unsigned long long)(clock64() - cjob0);
+            }
             stamp(j, 2);
             if (!last_job && !grid_dep(true, gridDim.x)) break;
             stamp(j, 3);
         } else if (jb.type == TL_JOB_ATTN) {
-            // ---- RoPE (+ q/k norm) + KV append + split-KV attention over all CTAs, one (row, kv head) group at a time
+            // ---- RoPE (+ q/k norm) + KV append + split-KV attention over all CTAs, one (row, kv head) group at a time.
+            // Inside a CTA warp r owns query head r of the group end to end (scores with lane = key, online softmax in
+            // registers, P.V with lane = output dims), so the only CTA-wide synchronisation is around the K/V tile in
+            // shared memory; the tile's global loads are issued before anything else and fly under the q round trip.
             const int n_h = jb.n_h, n_kv = jb.n_kv, D = jb.d, T_max = jb.T_max;
-            const int HALF = D >> 1, n_rep = n_h / n_kv, cap = p.chunk_cap;
+            const int HALF = D >> 1, n_rep = n_h / n_kv;
             const int G = n_kv * M;
             const int cpg = (int)gridDim.x / G;                       // CTAs per group (>= 1, checked on the host)
             const int grp = (int)blockIdx.x / cpg, split = (int)blockIdx.x % cpg;
@@ -451,22 +555,22 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_chain_kernel(const __gri
             const int b = in_grid ? grp / n_kv : 0, kvh = in_grid ? grp % n_kv : 0;
             const int pos = reinterpret_cast<const int32_t*>(jb.pos_dev)[(jb.flags & TL_ATTN_POS_PER_ROW) ? b : 0];
             const int n_keys = pos + 1;                               // cached keys 0..pos-1 + the new token
-            int cpg_eff = min(cpg, (n_keys + DC_MIN_KEYS - 1) / DC_MIN_KEYS);
-            const int chunk = (n_keys + cpg_eff - 1) / cpg_eff;
+            int cpg_eff = min(cpg, (n_keys + DC_TILE - 1) / DC_TILE);
+            const int chunk = (((n_keys + cpg_eff - 1) / cpg_eff) + DC_TILE - 1) / DC_TILE * DC_TILE;   // whole tiles
             cpg_eff = (n_keys + chunk - 1) / chunk;                   // no empty ranges
             const bool active = in_grid && split < cpg_eff;
-            float* sq = attn_s;                       // [8][128]
-            float* sk = sq + 8 * 128;                 // [128]
-            float* sv = sk + 128;                     // [128]
-            float* so = sv + 128;                     // [8][128]
-            float* sred = so + 8 * 128;               // [64]
-            float* sml = sred + 64;                   // [16]  (m, l) per query head
-            float* sc = sml + 16;                     // [n_rep][cap] scores / probabilities
+            float* sq = reinterpret_cast<float*>(attn_s);             // [8][128]
+            float* sk = sq + 8 * 128;                                 // [128]
+            float* sv = sk + 128;                                     // [128]
+            float* sp = sv + 128;                                     // [8][DC_TILE]
+            unsigned char* kt = reinterpret_cast<unsigned char*>(sp + 8 * DC_TILE);   // [DC_TILE][KT] bf16 rows, padded
+            unsigned char* vt = kt + DC_TILE * DC_KT_MAX;
+            const int KT = D * 2 + 16;                                // bytes per tile row
             if (tid == 0) s_last = 0;
             if (active) {
                 const int k0 = split * chunk, k1 = min(n_keys, k0 + chunk);
                 const bool owns_pos = k1 == n_keys;
-                const int nk = k1 - k0, nk_cached = owns_pos ? nk - 1 : nk;
+                const int n_tiles = (k1 - k0 + DC_TILE - 1) / DC_TILE;
                 const int heads = n_h + 2 * n_kv;
                 const bf16* row = reinterpret_cast<const bf16*>(jb.x) + (size_t)b * heads * D;
                 const bf16* cos_tab = reinterpret_cast<const bf16*>(jb.cos_tab);
@@ -475,25 +579,47 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_chain_kernel(const __gri
                 const bf16* kn = reinterpret_cast<const bf16*>(jb.k_norm_w);
                 bf16* k_cache = reinterpret_cast<bf16*>(jb.k_cache);
                 bf16* v_cache = reinterpret_cast<bf16*>(jb.v_cache);
-                // -- A: q of the n_rep heads (warp u), k of the new token (warp n_rep) -> norm -> RoPE -> shared memory
+                const bf16* kb = k_cache + ((size_t)b * n_kv + kvh) * T_max * D;
+                const bf16* vb = v_cache + ((size_t)b * n_kv + kvh) * T_max * D;
+                // tile loader: thread -> (row, 8-element column) of the [32, D] tile; 2 rows per thread at d = 128
+                const int vpr = D >> 3, rpp = DC_CT / vpr, n_pass = DC_TILE / rpp;     // 16/16/2 or 8/32/1
+                const int l_row = tid / vpr, l_col = (tid % vpr) * 8;
+                uint4 kreg[2], vreg[2];
+                auto load_tile = [&](int t0) {           // keys t0 .. t0+31 of the cache (rows >= pos are not in the cache)
+#pragma unroll
+                    for (int ps = 0; ps < 2; ++ps) {
+                        kreg[ps] = make_uint4(0u, 0u, 0u, 0u);
+                        vreg[ps] = make_uint4(0u, 0u, 0u, 0u);
+                        const int key = t0 + ps * rpp + l_row;
+                        if (ps < n_pass && key < k1 && key < pos) {
+                            kreg[ps] = *reinterpret_cast<const uint4*>(kb + (size_t)key * D + l_col);
+                            vreg[ps] = *reinterpret_cast<const uint4*>(vb + (size_t)key * D + l_col);
+                        }
+                    }
+                };
+                load_tile(k0);                           // in flight while q / k are fetched and rotated
+                // -- q of the n_rep heads (warp u), k of the new token (warp n_rep) -> norm -> RoPE -> shared memory
                 for (int u = warp; u <= n_rep; u += DC_CW) {
                     const bool is_k = u == n_rep;
                     if (is_k && !owns_pos) continue;
                     const bf16* src = row + (size_t)(is_k ? n_h + kvh : kvh * n_rep + u) * D;
                     const bf16* nw = is_k ? kn : qn;
                     float* dst = is_k ? sk : sq + u * 128;
-                    float x1[2], x2[2];
+                    float x1[2], x2[2], cs[2], sn[2];
                     float ssq = 0.f;
 #pragma unroll
                     for (int t = 0; t < 2; ++t) {
                         const int i = lane + 32 * t;
-                        x1[t] = x2[t] = 0.f;
+                        x1[t] = x2[t] = cs[t] = sn[t] = 0.f;
                         if (i < HALF) {
                             x1[t] = dc_ldcg_bf16(src + i);
                             x2[t] = dc_ldcg_bf16(src + i + HALF);
-                            ssq += x1[t] * x1[t] + x2[t] * x2[t];
+                            cs[t] = bf2f(cos_tab[(size_t)pos * HALF + i]);
+                            sn[t] = bf2f(sin_tab[(size_t)pos * HALF + i]);
                         }
                     }
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) ssq += x1[t] * x1[t] + x2[t] * x2[t];
                     if (nw) {
                         const float r = 1.0f / sqrtf(warp_sum(ssq) / (float)D + jb.eps);
 #pragma unroll
@@ -509,9 +635,8 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_chain_kernel(const __gri
                     for (int t = 0; t < 2; ++t) {
                         const int i = lane + 32 * t;
                         if (i < HALF) {
-                            const float c = bf2f(cos_tab[(size_t)pos * HALF + i]), s = bf2f(sin_tab[(size_t)pos * HALF + i]);
-                            dst[i] = rbf(rbf(x1[t] * c) + rbf(-x2[t] * s));
-                            dst[i + HALF] = rbf(rbf(x2[t] * c) + rbf(x1[t] * s));
+                            dst[i] = rbf(rbf(x1[t] * cs[t]) + rbf(-x2[t] * sn[t]));
+                            dst[i + HALF] = rbf(rbf(x2[t] * cs[t]) + rbf(x1[t] * sn[t]));
                         }
                     }
                 }
@@ -522,154 +647,154 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_chain_kernel(const __gri
                     k_cache[off] = f2bf(sk[tid]);
                     v_cache[off] = f2bf(sv[tid]);
                 }
-                const bf16* kb = k_cache + ((size_t)b * n_kv + kvh) * T_max * D;
-                const bf16* vb = v_cache + ((size_t)b * n_kv + kvh) * T_max * D;
                 const float scale_log2 = jb.scale * 1.4426950408889634f;
-                // -- B: scores.  4 threads share a cached key (a quarter of the head dim each), all n_rep heads at once
-                {
-                    const int part = tid & 3, EP = D >> 2;
-                    for (int base = 0; base < nk_cached; base += DC_CT / 4) {
-                        const int kl = base + (tid >> 2);
-                        const bool ok = kl < nk_cached;
-                        float acc[8];
+                float m_run = -INFINITY, l_run = 0.f;
+                float o[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int t = 0; t < n_tiles; ++t) {
+                    const int t0 = k0 + t * DC_TILE;
+                    // -- stage the tile (rows of the new token come from sk / sv, rows past the range stay zero)
 #pragma unroll
-                        for (int r = 0; r < 8; ++r) acc[r] = 0.f;
-                        if (ok) {
-                            const uint4* kr = reinterpret_cast<const uint4*>(kb + (size_t)(k0 + kl) * D + part * EP);
-                            for (int c = 0; c < (EP >> 3); ++c) {
-                                const uint4 kv4 = kr[c];
-                                const uint32_t* k32 = reinterpret_cast<const uint32_t*>(&kv4);
-                                const float f0 = bf16_lo(k32[0]), f1 = bf16_hi(k32[0]), f2 = bf16_lo(k32[1]), f3 = bf16_hi(k32[1]);
-                                const float f4 = bf16_lo(k32[2]), f5 = bf16_hi(k32[2]), f6 = bf16_lo(k32[3]), f7 = bf16_hi(k32[3]);
+                    for (int ps = 0; ps < 2; ++ps) {
+                        if (ps < n_pass) {
+                            const int r_ = ps * rpp + l_row, key = t0 + r_;
+                            if (key == pos && key < k1) {
+                                uint4 kk, vv;
+                                uint32_t* k32 = reinterpret_cast<uint32_t*>(&kk);
+                                uint32_t* v32 = reinterpret_cast<uint32_t*>(&vv);
 #pragma unroll
-                                for (int r = 0; r < 8; ++r) {
-                                    if (r < n_rep) {
-                                        const float4 qa = *reinterpret_cast<const float4*>(&sq[r * 128 + part * EP + c * 8]);
-                                        const float4 qb = *reinterpret_cast<const float4*>(&sq[r * 128 + part * EP + c * 8 + 4]);
-                                        acc[r] += f0 * qa.x + f1 * qa.y + f2 * qa.z + f3 * qa.w + f4 * qb.x + f5 * qb.y + f6 * qb.z + f7 * qb.w;
+                                for (int q = 0; q < 4; ++q) {
+                                    k32[q] = pack_bf16(sk[l_col + 2 * q], sk[l_col + 2 * q + 1]);
+                                    v32[q] = pack_bf16(sv[l_col + 2 * q], sv[l_col + 2 * q + 1]);
+                                }
+                                kreg[ps] = kk;
+                                vreg[ps] = vv;
+                            }
+                            *reinterpret_cast<uint4*>(kt + (size_t)r_ * KT + l_col * 2) = kreg[ps];
+                            *reinterpret_cast<uint4*>(vt + (size_t)r_ * KT + l_col * 2) = vreg[ps];
+                        }
+                    }
+                    if (t + 1 < n_tiles) load_tile(t0 + DC_TILE);     // next tile's loads fly under this tile's math
+                    dc_bar(1, DC_CT);
+                    if (warp < n_rep) {
+                        const int r = warp;
+                        // scores: lane = key of the tile
+                        float acc = 0.f;
+                        const unsigned char* krow = kt + (size_t)lane * KT;
+                        for (int c = 0; c < (D >> 3); ++c) {
+                            const uint4 kv4 = *reinterpret_cast<const uint4*>(krow + c * 16);
+                            const uint32_t* k32 = reinterpret_cast<const uint32_t*>(&kv4);
+                            const float4 qa = *reinterpret_cast<const float4*>(&sq[r * 128 + c * 8]);
+                            const float4 qb = *reinterpret_cast<const float4*>(&sq[r * 128 + c * 8 + 4]);
+                            acc += bf16_lo(k32[0]) * qa.x + bf16_hi(k32[0]) * qa.y + bf16_lo(k32[1]) * qa.z + bf16_hi(k32[1]) * qa.w +
+                                   bf16_lo(k32[2]) * qb.x + bf16_hi(k32[2]) * qb.y + bf16_lo(k32[3]) * qb.z + bf16_hi(k32[3]) * qb.w;
+                        }
+                        const bool in_range = t0 + lane < k1;
+                        const float sc_ = in_range ? acc * scale_log2 : -INFINITY;
+                        const float m_new = fmaxf(m_run, warp_max(sc_));          // finite: a tile always holds >= 1 key
+                        const float pr = in_range ? exp2f(sc_ - m_new) : 0.f;
+                        const float alpha = exp2f(m_run - m_new);                 // 0 on the first tile (m_run = -inf)
+                        l_run = l_run * alpha + warp_sum(pr);
+                        m_run = m_new;
+                        sp[r * DC_TILE + lane] = rbf(pr);       // P is cast to bf16 before P.V (SDPA contract); l keeps fp32
+                        __syncwarp();
+                        // P.V: lane = D/32 output dims
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) o[q] *= alpha;
+                        if (D == 128) {
+#pragma unroll 8
+                            for (int key = 0; key < DC_TILE; ++key) {
+                                const uint2 vv = *reinterpret_cast<const uint2*>(vt + (size_t)key * KT + lane * 8);
+                                const float pk = sp[r * DC_TILE + key];
+                                o[0] = fmaf(pk, bf16_lo(vv.x), o[0]);
+                                o[1] = fmaf(pk, bf16_hi(vv.x), o[1]);
+                                o[2] = fmaf(pk, bf16_lo(vv.y), o[2]);
+                                o[3] = fmaf(pk, bf16_hi(vv.y), o[3]);
+                            }
+                        } else {
+#pragma unroll 8
+                            for (int key = 0; key < DC_TILE; ++key) {
+                                const uint32_t vv = *reinterpret_cast<const uint32_t*>(vt + (size_t)key * KT + lane * 4);
+                                const float pk = sp[r * DC_TILE + key];
+                                o[0] = fmaf(pk, bf16_lo(vv), o[0]);
+                                o[1] = fmaf(pk, bf16_hi(vv), o[1]);
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    if (t + 1 < n_tiles) dc_bar(1, DC_CT);          // the next staging overwrites the tile
+                }
+                const int EPL = D >> 5;                              // output dims per lane (4 or 2)
+                if (cpg_eff == 1) {
+                    // the only CTA of its group: the attention output of its heads goes out directly
+                    if (warp < n_rep) {
+                        bf16* yo = reinterpret_cast<bf16*>(jb.y) + ((size_t)b * n_h + kvh * n_rep + warp) * D + lane * EPL;
+                        const float inv = 1.0f / l_run;
+                        *reinterpret_cast<uint32_t*>(yo) = pack_bf16(o[0] * inv, o[1] * inv);
+                        if (D == 128) *reinterpret_cast<uint32_t*>(yo + 2) = pack_bf16(o[2] * inv, o[3] * inv);
+                    }
+                    if (tid == 0) s_last = 1;
+                } else {
+                    // publish this CTA's partial (o unnormalised, m, l) per query head
+                    if (warp < n_rep) {
+                        float* pp = p.attn_part + (((size_t)b * n_h + kvh * n_rep + warp) * cpg + split) * (D + 4);
+                        if (D == 128) *reinterpret_cast<float4*>(pp + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
+                        else *reinterpret_cast<float2*>(pp + lane * 2) = make_float2(o[0], o[1]);
+                        if (lane == 0) { pp[D] = m_run; pp[D + 1] = l_run; }
+                    }
+                    dc_bar(1, DC_CT);
+                    if (tid == 0) {
+                        __threadfence();
+                        const unsigned old = atomicAdd(&grp_ctr[grp], 1u);
+                        if (old == (unsigned)(cpg_eff - 1)) {
+                            __threadfence();
+                            s_last = 1;
+                        }
+                    }
+                    dc_bar(1, DC_CT);
+                    if (s_last) {
+                        // the last CTA of the group combines the partials of all key ranges (batches of 4 independent loads)
+                        if (warp < n_rep) {
+                            const int h = kvh * n_rep + warp;
+                            const float* base = p.attn_part + ((size_t)b * n_h + h) * cpg * (D + 4);
+                            float mc = -INFINITY, L = 0.f, O[4] = {0.f, 0.f, 0.f, 0.f};
+                            for (int s0 = 0; s0 < cpg_eff; s0 += 4) {
+                                float ms[4], ls[4], os[4][4];
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const int s_ = min(s0 + q, cpg_eff - 1);
+                                    const float* e = base + (size_t)s_ * (D + 4);
+                                    ms[q] = __ldcg(e + D);
+                                    ls[q] = __ldcg(e + D + 1);
+                                    if (D == 128) {
+                                        const float4 t4 = __ldcg(reinterpret_cast<const float4*>(e + lane * 4));
+                                        os[q][0] = t4.x; os[q][1] = t4.y; os[q][2] = t4.z; os[q][3] = t4.w;
+                                    } else {
+                                        const float2 t2 = __ldcg(reinterpret_cast<const float2*>(e + lane * 2));
+                                        os[q][0] = t2.x; os[q][1] = t2.y; os[q][2] = os[q][3] = 0.f;
+                                    }
+                                }
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    if (s0 + q < cpg_eff) {
+                                        const float mn = fmaxf(mc, ms[q]);
+                                        const float a = exp2f(mc - mn), w = exp2f(ms[q] - mn);
+                                        L = L * a + w * ls[q];
+#pragma unroll
+                                        for (int e_ = 0; e_ < 4; ++e_) O[e_] = O[e_] * a + w * os[q][e_];
+                                        mc = mn;
                                     }
                                 }
                             }
+                            bf16* yo = reinterpret_cast<bf16*>(jb.y) + ((size_t)b * n_h + h) * D + lane * EPL;
+                            const float inv = 1.0f / L;
+                            *reinterpret_cast<uint32_t*>(yo) = pack_bf16(O[0] * inv, O[1] * inv);
+                            if (D == 128) *reinterpret_cast<uint32_t*>(yo + 2) = pack_bf16(O[2] * inv, O[3] * inv);
                         }
-#pragma unroll
-                        for (int r = 0; r < 8; ++r) {
-                            if (r < n_rep) {
-                                float v = acc[r];
-                                v += __shfl_xor_sync(0xffffffffu, v, 1);
-                                v += __shfl_xor_sync(0xffffffffu, v, 2);
-                                if (ok && part == 0) sc[r * cap + kl] = v * scale_log2;
-                            }
-                        }
+                        if (tid == 0) grp_ctr[grp] = 0u;
                     }
-                    if (owns_pos) {                              // the new token's key comes from shared memory
-                        for (int r = warp; r < n_rep; r += DC_CW) {
-                            float acc = 0.f;
-                            for (int i = lane; i < D; i += 32) acc += sq[r * 128 + i] * sk[i];
-                            acc = warp_sum(acc) * scale_log2;
-                            if (lane == 0) sc[r * cap + nk - 1] = acc;
-                        }
-                    }
-                }
-                dc_bar(1, DC_CT);
-                // -- C: per-head softmax over this CTA's key range (P rounded to bf16 before P.V: SDPA contract)
-                for (int r = warp; r < n_rep; r += DC_CW) {
-                    float mx = -INFINITY;
-                    for (int kl = lane; kl < nk; kl += 32) mx = fmaxf(mx, sc[r * cap + kl]);
-                    mx = warp_max(mx);
-                    float l = 0.f;
-                    for (int kl = lane; kl < nk; kl += 32) {
-                        const float pr = exp2f(sc[r * cap + kl] - mx);
-                        l += pr;
-                        sc[r * cap + kl] = rbf(pr);
-                    }
-                    l = warp_sum(l);
-                    if (lane == 0) { sml[2 * r] = mx; sml[2 * r + 1] = l; }
-                }
-                dc_bar(1, DC_CT);
-                // -- D: P.V.  wph warps per head share the keys; a lane owns D/32 output dims
-                {
-                    const int wph = max(1, DC_CW / n_rep), r = warp / wph, sub = warp % wph;
-                    if (r < n_rep) {
-                        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                        if (D == 128) {
-                            for (int kl = sub; kl < nk_cached; kl += wph) {
-                                const uint2 vv = *reinterpret_cast<const uint2*>(vb + (size_t)(k0 + kl) * D + lane * 4);
-                                const float pr = sc[r * cap + kl];
-                                acc[0] = fmaf(pr, bf16_lo(vv.x), acc[0]);
-                                acc[1] = fmaf(pr, bf16_hi(vv.x), acc[1]);
-                                acc[2] = fmaf(pr, bf16_lo(vv.y), acc[2]);
-                                acc[3] = fmaf(pr, bf16_hi(vv.y), acc[3]);
-                            }
-                            if (owns_pos && sub == 0) {
-                                const float pr = sc[r * cap + nk - 1];
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) acc[q] = fmaf(pr, sv[lane * 4 + q], acc[q]);
-                            }
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) so[(sub * n_rep + r) * 128 + lane * 4 + q] = acc[q];
-                        } else {   // D == 64
-                            for (int kl = sub; kl < nk_cached; kl += wph) {
-                                const uint32_t vv = *reinterpret_cast<const uint32_t*>(vb + (size_t)(k0 + kl) * D + lane * 2);
-                                const float pr = sc[r * cap + kl];
-                                acc[0] = fmaf(pr, bf16_lo(vv), acc[0]);
-                                acc[1] = fmaf(pr, bf16_hi(vv), acc[1]);
-                            }
-                            if (owns_pos && sub == 0) {
-                                const float pr = sc[r * cap + nk - 1];
-                                acc[0] = fmaf(pr, sv[lane * 2], acc[0]);
-                                acc[1] = fmaf(pr, sv[lane * 2 + 1], acc[1]);
-                            }
-                            so[(sub * n_rep + r) * 128 + lane * 2] = acc[0];
-                            so[(sub * n_rep + r) * 128 + lane * 2 + 1] = acc[1];
-                        }
-                    }
-                }
-                dc_bar(1, DC_CT);
-                // -- E: publish this CTA's partial (o unnormalised, m, l) per query head
-                {
-                    const int wph = max(1, DC_CW / n_rep);
-                    for (int idx = tid; idx < n_rep * D; idx += DC_CT) {
-                        const int r = idx / D, dd = idx % D;
-                        float o = 0.f;
-                        for (int s = 0; s < wph; ++s) o += so[(s * n_rep + r) * 128 + dd];
-                        p.attn_part[(((size_t)b * n_h + kvh * n_rep + r) * cpg + split) * (D + 2) + dd] = o;
-                    }
-                    if (tid < n_rep) {
-                        float* pp = p.attn_part + (((size_t)b * n_h + kvh * n_rep + tid) * cpg + split) * (D + 2) + D;
-                        pp[0] = sml[2 * tid];
-                        pp[1] = sml[2 * tid + 1];
-                    }
-                }
-                dc_bar(1, DC_CT);
-                if (tid == 0) {
-                    __threadfence();
-                    const unsigned old = atomicAdd(&grp_ctr[grp], 1u);
-                    if (old == (unsigned)(cpg_eff - 1)) {
-                        __threadfence();
-                        s_last = 1;
-                    }
-                }
-                dc_bar(1, DC_CT);
-                if (s_last) {
-                    // -- F: the last CTA of the group combines the partials of all key ranges and writes the attention
-                    //       output of its n_rep heads; then the group counter is ready for the next launch
-                    for (int idx = tid; idx < n_rep * D; idx += DC_CT) {
-                        const int r = idx / D, dd = idx % D, h = kvh * n_rep + r;
-                        const float* base = p.attn_part + ((size_t)b * n_h + h) * cpg * (D + 2);
-                        float m = -INFINITY;
-                        for (int s = 0; s < cpg_eff; ++s) m = fmaxf(m, __ldcg(base + (size_t)s * (D + 2) + D));
-                        float L = 0.f, O = 0.f;
-                        for (int s = 0; s < cpg_eff; ++s) {
-                            const float w = exp2f(__ldcg(base + (size_t)s * (D + 2) + D) - m);
-                            L = fmaf(w, __ldcg(base + (size_t)s * (D + 2) + D + 1), L);
-                            O = fmaf(w, __ldcg(base + (size_t)s * (D + 2) + dd), O);
-                        }
-                        reinterpret_cast<bf16*>(jb.y)[((size_t)b * n_h + h) * D + dd] = f2bf(O / L);
-                    }
-                    if (tid == 0) grp_ctr[grp] = 0u;
                 }
             }
-            // one arrival per (row, kv head) group, by the CTA that combined it; everybody waits for all groups
+            // one arrival per (row, kv head) group, by the CTA that wrote its output; everybody waits for all groups
             stamp(j, 2);
             if (!last_job && !grid_dep(s_last != 0, (unsigned)G)) break;
             stamp(j, 3);
@@ -684,6 +809,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_chain_kernel(const __gri
         if (prev == gridDim.x - 1) {
             p.sync[0] = 0;
             p.sync[1] = 0;
+            for (int j = 0; j < p.n_jobs; ++j) p.sync[DC_JOBCTR + j] = 0;
             __threadfence();
         }
     }
@@ -693,7 +819,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_chain_kernel(const __gri
 
 static unsigned long long* g_chain_trace = nullptr;
 static int g_chain_trace_slots = 0, g_chain_trace_next = 0;
-constexpr int DC_TRACE_WORDS = 2 * (tl::DC_MAX_JOBS + 1) * 4;
+constexpr int DC_TRACE_WORDS = tl::DC_STAT_OFF + tl::DC_MAX_JOBS * 4;
 
 extern "C" {
 
@@ -708,10 +834,10 @@ int tl_decode_chain_trace(void* buf, int n_slots) {
 }
 
 size_t tl_decode_chain_ws(int M, int n_h, int n_kv, int d) {
-    // attention partials [M*n_h][cpg][d+2] floats with cpg = CTAs / (n_kv*M) <= 160 / (n_kv*M) on any sm_100 part
+    // attention partials [M*n_h][cpg][d+4] floats with cpg = CTAs / (n_kv*M) <= 160 / (n_kv*M) on any sm_100 part
     if (M < 1 || n_h < 1 || n_kv < 1) return 0;
     const int cpg = 160 / (n_kv * M) > 0 ? 160 / (n_kv * M) : 1;
-    return (size_t)M * n_h * cpg * (d + 2) * sizeof(float) + 256;
+    return (size_t)M * n_h * cpg * (d + 4) * sizeof(float) + 256;
 }
 
 int tl_decode_chain(const tl_decode_job* jobs, int n_jobs, int M, void* sync_slot, void* attn_ws, size_t attn_ws_bytes,
@@ -721,7 +847,7 @@ int tl_decode_chain(const tl_decode_job* jobs, int n_jobs, int M, void* sync_slo
     TL_REQUIRE(jobs && n_jobs > 0 && n_jobs <= DC_MAX_JOBS && sync_slot, TL_ERR_INVALID, "tl_decode_chain: bad job list (n=%d, max %d)",
                n_jobs, DC_MAX_JOBS);
     const int grid = sm_count();
-    int k_max = 0, chunk_cap = 0, n_attn = 0;
+    int k_max = 0, n_attn = 0;
     for (int j = 0; j < n_jobs; ++j) {
         const tl_decode_job& jb = jobs[j];
         if (jb.type == TL_JOB_GEMV) {
@@ -734,19 +860,23 @@ int tl_decode_chain(const tl_decode_job* jobs, int n_jobs, int M, void* sync_slo
             const int G = jb.n_kv * M;
             TL_REQUIRE(G <= grid && G <= 60, TL_ERR_INVALID, "tl_decode_chain: %d (row, kv head) groups do not fit", G);
             const int cpg = grid / G;
-            const int cap = max(DC_MIN_KEYS, (jb.T_max + cpg - 1) / cpg);
-            if (cap > chunk_cap) chunk_cap = cap;
-            TL_REQUIRE(attn_ws && attn_ws_bytes >= (size_t)M * jb.n_h * cpg * (jb.d + 2) * sizeof(float), TL_ERR_INVALID,
+            TL_REQUIRE(attn_ws && attn_ws_bytes >= (size_t)M * jb.n_h * cpg * (jb.d + 4) * sizeof(float), TL_ERR_INVALID,
                        "tl_decode_chain: attention workspace too small");
             ++n_attn;
         } else {
             TL_REQUIRE(false, TL_ERR_INVALID, "tl_decode_chain: job %d has unsupported type %d", j, jb.type);
         }
     }
-    chunk_cap = (chunk_cap + 3) & ~3;
+    (void)n_attn;
     constexpr int SMEM_CAP = 227 * 1024 - 1024;       // static shared memory of the kernel stays below 1 KB
+    static int DC_STAGE = 0;
+    if (!DC_STAGE) {
+        const char* e = getenv("TL_CHAIN_STAGE_KB");      // ring slot size: 16 (default) or 8 KB (more, smaller slots: all 8
+        DC_STAGE = (e && atoi(e) == 8) ? 8192 : 16384;    // consumer warps get a slot class of their own)
+    }
+    const int DC_KC = DC_STAGE / 4;
     const size_t xs_bytes = (((size_t)M * k_max * 2) + 127) & ~(size_t)127;
-    const size_t attn_bytes = (size_t)(DC_ATTN_FIXED + 8 * chunk_cap) * sizeof(float);
+    const size_t attn_bytes = (size_t)DC_ATTN_BYTES;
     const size_t fixed = xs_bytes + attn_bytes + 2 * DC_MAX_STAGES * sizeof(uint64_t);
     TL_REQUIRE(fixed + 4 * DC_STAGE <= (size_t)SMEM_CAP, TL_ERR_INVALID, "tl_decode_chain: M*K_max / context too large (%zu B fixed)", fixed);
     int max_stages = (int)((SMEM_CAP - fixed) / DC_STAGE);
@@ -761,7 +891,18 @@ int tl_decode_chain(const tl_decode_job* jobs, int n_jobs, int M, void* sync_slo
     prm.n_stages = n_stages;
     prm.NW = NW;
     prm.xs_bytes = (int)xs_bytes;
-    prm.chunk_cap = chunk_cap;
+    static int dyn = -1, l2_ahead = -1;
+    if (dyn < 0) {
+        const char* e = getenv("TL_CHAIN_DYNAMIC");      // 1: units handed out by ticket counters instead of the static split
+        dyn = (e && e[0] == '1') ? 1 : 0;                // (measured worse: a ticket covers NW units, too coarse at the tail)
+        const char* a = getenv("TL_CHAIN_L2_AHEAD_KB");  // L2 prefetch lead per CTA
+        l2_ahead = a ? atoi(a) * 1024 : 192 * 1024;
+        if (l2_ahead < 0) l2_ahead = 0;
+    }
+    prm.dynamic = dyn;
+    prm.stage_bytes = DC_STAGE;
+    prm.kc = DC_KC;
+    prm.l2_ahead = l2_ahead;
     prm.sync = (unsigned*)sync_slot;
     prm.attn_part = (float*)attn_ws;
     prm.pf_ptr = (const unsigned char*)pf_ptr;

@@ -71,24 +71,59 @@ def _check_unconsumed(kwargs: dict, what: str):
 
 
 def _check_attention_mask(mask, shape):
-    """Only the all-ones mask (no padding) is accepted; a mask with zeros means left/right-padded prompts, whose rows
-    would otherwise attend to pad tokens at shifted positions."""
+    """forward(): only the all-ones mask (no padding) is accepted; a mask with zeros means padded prompts, whose rows
+    would otherwise attend to pad tokens at shifted positions.  (``generate`` handles left-padded batches.)"""
     if mask is None:
         return
     if tuple(mask.shape) != tuple(shape):
         raise ValueError(f"attention_mask shape {tuple(mask.shape)} != input_ids shape {tuple(shape)}")
     if not bool((mask != 0).all()):
-        raise NotImplementedError("padded prompts (attention_mask with zeros) are not supported: pass rows of equal "
-                                  "length, or generate ragged rows one micro-batch at a time")
+        raise NotImplementedError("padded rows (attention_mask with zeros) are not supported by forward(): pass rows of "
+                                  "equal length")
+
+
+def _left_pad_groups(mask: torch.Tensor):
+    """A left-padded batch (HF's convention for generation: ``tokenizer(..., padding=True, padding_side='left')``)
+    as {real length: [row indices]}; None when no row is padded.  Right padding / holes raise."""
+    m = (mask != 0).cpu()
+    if bool(m.all()):
+        return None
+    S = m.shape[1]
+    lengths = m.sum(1)
+    want = torch.arange(S)[None, :] >= (S - lengths)[:, None]           # zeros, then ones
+    if not torch.equal(m, want) or int(lengths.min()) == 0:
+        raise NotImplementedError("attention_mask must describe LEFT-padded prompts (zeros, then ones; at least one token per row)")
+    groups = {}
+    for r, L in enumerate(lengths.tolist()):
+        groups.setdefault(int(L), []).append(r)
+    return groups
+
+
+EOS_CHECK_EVERY = 16       # decode steps between two host-side "has every row emitted EOS?" checks
+
+
+def _eos_list(eos_token_id):
+    if eos_token_id is None:
+        return []
+    return [int(e) for e in eos_token_id] if isinstance(eos_token_id, (list, tuple)) else [int(eos_token_id)]
+
+
+def _all_rows_finished(tokens: torch.Tensor, eos_ids) -> bool:
+    """tokens [rows, cols] generated so far: True once every row holds an EOS (one small device reduction + sync)."""
+    hit = torch.zeros_like(tokens, dtype=torch.bool)
+    for e in eos_ids:
+        hit |= tokens == e
+    return bool(hit.any(1).all().item())
 
 
 def apply_eos(result: torch.Tensor, prompt_len: int, eos_token_id=None, pad_token_id=None) -> torch.Tensor:
-    """HF ``generate`` stopping semantics applied to a finished greedy generation [B, S+new]: everything after a row's
-    first EOS becomes ``pad_token_id`` (default: the EOS id) and the result ends where the last row finished.
-    (The decode loop itself always runs ``max_new_tokens`` steps: the host never sees a token while they run.)"""
+    """HF ``generate`` stopping semantics applied to a generation [B, S+new]: everything after a row's first EOS
+    becomes ``pad_token_id`` (default: the EOS id) and the result ends where the last row finished.  (The decode loop
+    checks every ``EOS_CHECK_EVERY`` steps whether all rows are finished and stops computing then; the at most 15 surplus
+    columns are cut here.)"""
     if eos_token_id is None:
         return result
-    eos_ids = [int(e) for e in eos_token_id] if isinstance(eos_token_id, (list, tuple)) else [int(eos_token_id)]
+    eos_ids = _eos_list(eos_token_id)
     pad = eos_ids[0] if pad_token_id is None else int(pad_token_id)
     new = result[:, prompt_len:]
     if new.shape[1] == 0:
@@ -281,6 +316,8 @@ class DistributedModel(torch.nn.Module):
         span = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         span[0].record()
         step_done = []
+        eos_ids = _eos_list(self._eos[0])
+        n_cols = max_new                              # token columns that will exist when the loop ends
         for step in range(max_new):
             for m in range(n_mb):
                 if step < max_new - 1:
@@ -292,6 +329,17 @@ class DistributedModel(torch.nn.Module):
                 ev = torch.cuda.Event()
                 ev.record()
                 step_done.append(ev)
+            if eos_ids and step < max_new - 1 and (step + 1) % EOS_CHECK_EVERY == 0:
+                # HF stops once every row has emitted EOS.  Columns 0..step are logged on the first stage; all ranks
+                # drain their queues (no persistent kernel is in flight during the collective) and agree on stopping.
+                torch.cuda.synchronize(dev)
+                flag = torch.zeros(1, dtype=torch.int32, device=dev)
+                if link.first and _all_rows_finished(ring.out_log[:n_mb, :b, :step + 1].reshape(B, step + 1), eos_ids):
+                    flag.fill_(1)
+                link.broadcast(flag, 0)
+                if int(flag.item()):
+                    n_cols = step + 1
+                    break
         span[1].record()
         if streamer is not None and link.first:
             for step, ev in enumerate(step_done):                  # step's graph logged column `step` before its event
@@ -305,15 +353,44 @@ class DistributedModel(torch.nn.Module):
             self.timers["decode_span_s"] = span[0].elapsed_time(span[1]) * 1e-3
             self.timers["decode_busy_s"] = self.timers["decode_span_s"] - float(ring.wait_ns.item()) * 1e-9
         if link.first:
-            out_tokens = ring.out_log[:n_mb, :b, :max_new].reshape(B, max_new)
+            out_tokens = ring.out_log[:n_mb, :b, :n_cols].reshape(B, n_cols)
             result = torch.cat([input_ids.to(dev), out_tokens], dim=1)
         else:
-            result = torch.empty(B, S + max_new, dtype=torch.int64, device=dev)
+            result = torch.empty(B, S + n_cols, dtype=torch.int64, device=dev)
         link.broadcast(result, 0)
         if streamer is not None and link.first:
             streamer.end()
         self.timers["generate_wall_s"] = time.perf_counter() - t0
         return apply_eos(result, S, *self._eos)
+
+    def _generate_left_padded(self, input_ids, groups, max_new, streamer, use_graph, sampling):
+        """HF semantics for a left-padded batch: every row attends to its own tokens only, at positions 0..L-1.  Rows of
+        equal real length are generated together (one uniform run per length: the KV cache and RoPE positions of a run
+        start at the row's first real token, so no pad key exists to be masked); the result keeps HF's layout
+        [pads | prompt | new tokens | pad_token_id...]."""
+        if streamer is not None:
+            raise NotImplementedError("streamer with a padded batch (rows finish in separate runs)")
+        eos, pad = self._eos
+        pad_id = pad if pad is not None else (_eos_list(eos)[0] if eos is not None else 0)
+        first = self.link.first
+        B, S = (input_ids.shape if first else (sum(len(r) for r in groups.values()), max(groups)))
+        out = torch.full((B, S + max_new), int(pad_id), dtype=torch.int64, device=self.device)
+        if first:
+            out[:, :S] = input_ids.to(self.device)
+        longest = 0
+        for L in sorted(groups):
+            rows = groups[L]
+            sub = input_ids[rows][:, S - L:].contiguous() if first else None
+            kw = dict(max_new_tokens=max_new, use_graph=use_graph, eos_token_id=eos, pad_token_id=pad)
+            if sampling is not None:
+                kw.update(do_sample=True, temperature=sampling["temperature"], top_k=sampling["top_k"], top_p=sampling["top_p"],
+                          seed=sampling["seed"] + L)
+            got = self.generate(sub, **kw)
+            n_new = got.shape[1] - L
+            out[torch.as_tensor(rows, device=self.device), S:S + n_new] = got[:, L:].to(self.device)
+            longest = max(longest, n_new)
+        self._eos = (eos, pad)
+        return out[:, :S + longest]
 
     # ------------------------------------------------------------------------------------------ generate
     @torch.no_grad()
@@ -339,12 +416,18 @@ class DistributedModel(torch.nn.Module):
             if sampling["temperature"] <= 0 or not (0 < sampling["top_p"] <= 1) or sampling["top_k"] < 0:
                 raise ValueError(f"invalid sampling parameters {sampling}")
         self._eos = (kwargs.pop("eos_token_id", None), kwargs.pop("pad_token_id", None))
-        if self.link.first and input_ids is not None:
-            _check_attention_mask(kwargs.pop("attention_mask", None), input_ids.shape)
-        else:
-            kwargs.pop("attention_mask", None)
+        mask = kwargs.pop("attention_mask", None)
         _check_unconsumed(kwargs, "DistributedModel.generate")
         link, st, cfg = self.link, self.stage, self.cfg
+        groups = None
+        if link.first and mask is not None:
+            if tuple(mask.shape) != tuple(input_ids.shape):
+                raise ValueError(f"attention_mask shape {tuple(mask.shape)} != input_ids shape {tuple(input_ids.shape)}")
+            groups = _left_pad_groups(mask)
+        if self.world > 1:
+            groups = link.broadcast_object(groups)
+        if groups is not None:
+            return self._generate_left_padded(input_ids, groups, max_new, streamer, use_graph, sampling)
         shape, sampling = link.broadcast_object((tuple(input_ids.shape), sampling) if link.first else None)
         B, S = shape
         if hasattr(st, "set_sampling"):
@@ -354,8 +437,8 @@ class DistributedModel(torch.nn.Module):
         elif sampling is not None:
             raise NotImplementedError("sampling needs the CUDA stage")
         n_mb = min(self.n_pipelines, B)
-        if B % n_mb:
-            raise ValueError(f"batch {B} not divisible into {n_mb} micro-batches")
+        while B % n_mb:                      # the largest micro-batch count <= n_pipelines that divides the batch
+            n_mb -= 1
         b = B // n_mb
         if b > st.max_batch or S + max_new > st.max_seq:
             raise ValueError(f"stage sized for micro-batch<={st.max_batch}, T<={st.max_seq}; got {b}, {S + max_new}")
@@ -401,7 +484,21 @@ class DistributedModel(torch.nn.Module):
         if profile:
             span = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             span[0].record()
+        eos_ids = _eos_list(self._eos[0])
+        n_cols = max_new
         for step in range(max_new):
+            if eos_ids and step and step % EOS_CHECK_EVERY == 0:
+                # columns 0..step-1 are complete on the first stage: stop once every row has emitted EOS (HF semantics)
+                flag = torch.zeros(1, dtype=torch.int32, device=dev)
+                if link.first and _all_rows_finished(out_tokens[:, :step], eos_ids):
+                    flag.fill_(1)
+                if multi:
+                    link.flush()
+                    torch.cuda.synchronize(dev)
+                    link.broadcast(flag, 0)
+                if int(flag.item()):
+                    n_cols = step
+                    break
             for m in range(n_mb):
                 if link.first:
                     if multi:
@@ -435,9 +532,9 @@ class DistributedModel(torch.nn.Module):
             self.timers["decode_span_s"] = span[0].elapsed_time(span[1]) * 1e-3
             self.timers["decode_busy_s"] = sum(a.elapsed_time(b_) for a, b_ in prof_events) * 1e-3
         if link.first:
-            result = torch.cat([input_ids.to(dev), out_tokens], dim=1)
+            result = torch.cat([input_ids.to(dev), out_tokens[:, :n_cols]], dim=1)
         else:
-            result = torch.empty(B, S + max_new, dtype=torch.int64, device=dev)
+            result = torch.empty(B, S + n_cols, dtype=torch.int64, device=dev)
         link.broadcast(result, 0)
         if hasattr(st, "check"):
             st.check()

@@ -507,7 +507,7 @@ def decode_chain_ws(M: int, n_h: int, n_kv: int, d: int) -> int:
     return int(load().tl_decode_chain_ws(M, n_h, n_kv, d))
 
 
-CHAIN_TRACE_WORDS = 2 * (CHAIN_MAX_JOBS + 1) * 4
+CHAIN_TRACE_WORDS = 2 * (CHAIN_MAX_JOBS + 1) * 4 + CHAIN_MAX_JOBS * 160 + CHAIN_MAX_JOBS * 4
 
 
 def decode_chain_trace(buf: Optional[torch.Tensor]):

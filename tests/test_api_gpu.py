@@ -48,9 +48,49 @@ def test_generate_edge_cases():
     with pytest.raises(ValueError):
         dm.generate(synthetic_tokens(cfg, 4, 4), max_new_tokens=2)           # more rows than the stage was sized for
     with pytest.raises(NotImplementedError):
-        dm.generate(one, max_new_tokens=2, do_sample=True)
+        dm.generate(one, max_new_tokens=2, num_beams=4)                      # unsupported HF keywords are refused, not dropped
+    with pytest.raises(NotImplementedError):
+        dm(one, position_ids=torch.zeros(1, 1, dtype=torch.long))
+    with pytest.raises(NotImplementedError):
+        dm(synthetic_tokens(cfg, 2, 4), attention_mask=torch.tensor([[0, 1, 1, 1], [1, 1, 1, 1]]))   # forward: no padded rows
+    assert dm.generate(one, max_new_tokens=2, use_cache=True, num_beams=1).shape == (1, 3)           # neutral values pass
     with pytest.raises(NotImplementedError):
         DistributedModel(cfg, training=False, dtype=torch.float32)
+
+
+def test_generate_left_padded_batch_and_eos_early_stop():
+    """Batched-generation conventions of HF: a left-padded batch with its attention_mask (every row attends to its own
+    tokens at positions 0..L-1; the result keeps the pads in front) and stopping once every row has emitted EOS."""
+    from tensorlink_b200.ml import DistributedModel
+    cfg = C.TINY_QWEN2_D128
+    sd = init_state_dict(cfg)
+    dm = DistributedModel(cfg, training=False, max_batch=4, max_seq=96)
+    lens, S, new, PAD = [9, 14, 9, 5], 14, 12, 7
+    rows = [synthetic_tokens(cfg, 1, L, seed=100 + i)[0] for i, L in enumerate(lens)]
+    ids = torch.full((4, S), PAD, dtype=torch.int64)
+    mask = torch.zeros(4, S, dtype=torch.int64)
+    for r, (t, L) in enumerate(zip(rows, lens)):
+        ids[r, S - L:], mask[r, S - L:] = t, 1
+    out = dm.generate(ids, attention_mask=mask, max_new_tokens=new, pad_token_id=PAD).cpu()
+    assert out.shape == (4, S + new) and torch.equal(out[:, :S], ids)
+    oracle = O.OracleModel(cfg, sd, "sdpa_math")
+    for r, (t, L) in enumerate(zip(rows, lens)):
+        alone = dm.generate(t[None], max_new_tokens=new).cpu()                # the same row without padding
+        want, margins = oracle.generate(t[None], new, return_margins=True)
+        for s in range(new):                                                  # exact until the first unresolvable step
+            if margins[0, s] < 0.05:
+                break
+            assert out[r, S + s] == want[0, L + s] == alone[0, L + s], (r, s)
+    with pytest.raises(NotImplementedError):
+        dm.generate(ids, attention_mask=mask.flip(1), max_new_tokens=2)       # right padding is not a generation layout
+    # ---- EOS: take the token the model emits at step 2 as the EOS id; HF semantics = the result ends right after it
+    base = dm.generate(rows[1][None], max_new_tokens=40).cpu()
+    eos = int(base[0, 14 + 2])
+    got = dm.generate(rows[1][None], max_new_tokens=40, eos_token_id=eos).cpu()
+    first = int((base[0, 14:] == eos).nonzero()[0])
+    assert torch.equal(got, base[:, :14 + first + 1])
+    # the decode loop stopped at the first check after the EOS instead of running all 40 steps
+    assert int(dm.stage.slots[0].pos_dev.item()) <= 14 + 16
 
 
 def test_forward_kwargs_and_train_eval_switch():

@@ -73,7 +73,11 @@ def test_full_vocabulary_support_and_ties(nat):
     for kw in (dict(temperature=1.0, top_k=50, top_p=1.0), dict(temperature=0.9, top_k=0, top_p=0.8), dict(temperature=1.0, top_k=200, top_p=0.95)):
         probs = hf_warped_probs(logits, kw["temperature"], kw["top_k"], kw["top_p"])[0]
         ids = draw(nat, logits, 400, seed=9, **kw)[0]
-        assert bool((probs[ids] > 0).all()), kw
+        # HF's sort cuts INSIDE a group of tied logits at the top-p boundary (which members survive depends on its sort);
+        # the kernel keeps the whole boundary group: allowed = every token at least as large as HF's smallest survivor
+        floor = logits[0].float()[probs > 0].min()
+        assert bool((logits[0].float()[ids] >= floor).all()), kw
+        assert bool((probs[ids] > 0).float().mean() > 0.9), kw
         assert len(set(ids.tolist())) > 5
     one = draw(nat, logits, 8, temperature=1.0, top_k=1, top_p=1.0, seed=3)[0]
     top = logits[0].float()

@@ -42,7 +42,11 @@ def main():
         st.decode(0, args.rows)
     torch.cuda.synchronize()
     nat.decode_chain_trace(None)
-    t = trace[n_launch:2 * n_launch].cpu().view(n_launch, 2, nat.CHAIN_MAX_JOBS + 1, 4).double() * 1e-3   # us
+    raw = trace[n_launch:2 * n_launch].cpu()
+    head = 2 * (nat.CHAIN_MAX_JOBS + 1) * 4
+    t = raw[:, :head].reshape(n_launch, 2, nat.CHAIN_MAX_JOBS + 1, 4).double() * 1e-3   # us
+    done_all = raw[:, head:head + nat.CHAIN_MAX_JOBS * 160].reshape(n_launch, nat.CHAIN_MAX_JOBS, 160).double() * 1e-3
+    stat = raw[:, head + nat.CHAIN_MAX_JOBS * 160:].reshape(n_launch, nat.CHAIN_MAX_JOBS, 4).double()
     names = ["attn", "o", "gate_up", "down", "qkv_next"]
     print(f"{args.model}: {n_launch} chain launches per step, last replay; times in us relative to each launch's kernel entry (CTA 0)")
     for sel, who in ((0, "CTA 0"), (1, "last CTA")):
@@ -60,6 +64,19 @@ def main():
             m = rel.mean(0)
             print(f"  {nm:9s} start {m[0]:7.2f}  staged {m[1]:7.2f} (+{m[1] - m[0]:5.2f})  done {m[2]:7.2f} (+{m[2] - m[1]:6.2f})  "
                   f"dep passed {m[3]:7.2f} (+{m[3] - m[2]:5.2f})")
+    print("--- all CTAs: spread of the 'work done' time per job (us): last - first, last - median")
+    for j, nm in enumerate(names):
+        d = done_all[1:-1, j]
+        d = d[:, (d > 0).all(0)]
+        if d.numel() == 0:
+            continue
+        print(f"  {nm:9s} {float((d.max(1).values - d.min(1).values).mean()):6.2f} {float((d.max(1).values - d.median(1).values).mean()):6.2f}"
+              f"   dep passed - last done: {float((t[1:-1, 0, j, 3] - d.max(1).values).mean()):6.2f}")
+    print("--- CTA 0, cycles per job: consumer warp 0 waiting for weights / in the job loop; producer waiting for free ring slots")
+    for j, nm in enumerate(names):
+        c = stat[1:-1, j].mean(0)
+        if float(c[1]) > 0:
+            print(f"  {nm:9s} consumer wait {c[0]:9.0f} of {c[1]:9.0f} ({100 * c[0] / c[1]:5.1f} %)   producer wait {c[2]:9.0f}")
     ent = t[:, 0, -1, 0]
     ext = t[:, :, -1, 2].max(1).values
     print("launch period (entry to next entry): %.2f us; exit of launch i -> entry of launch i+1: %.2f us" % (
