@@ -43,6 +43,7 @@ constexpr int DC_MAX_STAGES = 24;
 constexpr int DC_MAX_JOBS = 16;
 constexpr int DC_MAX_M = 4;
 constexpr int DC_TILE = 32;                    // keys per attention tile (an attention CTA takes whole tiles)
+constexpr int DC_MIN_KEYS = 128;               // ... and at least this many keys: contexts up to here need no partials / combine
 constexpr int DC_KT_MAX = 128 * 2 + 16;        // bytes per K / V tile row at d = 128 (16 bytes of padding: conflict-free rows)
 // shared memory of the attention job: sq[8][128] f32 | sk[128] sv[128] f32 | sp[8][32] f32 | K tile | V tile
 constexpr int DC_ATTN_BYTES = 8 * 128 * 4 + 2 * 128 * 4 + 8 * DC_TILE * 4 + 2 * DC_TILE * DC_KT_MAX;
@@ -268,10 +269,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_chain_kernel(const __gri
     auto grid_dep = [&](bool arrive, unsigned n_arrivals) -> bool {
         dc_bar(1, DC_CT);                              // every consumer thread's stores of this job are issued
         if (tid == 0) {
-            if (arrive) {
-                __threadfence();
-                dc_red_release(bar_ctr, 1u);
-            }
+            if (arrive) dc_red_release(bar_ctr, 1u);      // release: everything the bar.sync above ordered before it
             bar_target += n_arrivals;
             unsigned long long t0 = 0;
             int it = 0;
@@ -555,7 +553,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) decode_chain_kernel(const __gri
             const int b = in_grid ? grp / n_kv : 0, kvh = in_grid ? grp % n_kv : 0;
             const int pos = reinterpret_cast<const int32_t*>(jb.pos_dev)[(jb.flags & TL_ATTN_POS_PER_ROW) ? b : 0];
             const int n_keys = pos + 1;                               // cached keys 0..pos-1 + the new token
-            int cpg_eff = min(cpg, (n_keys + DC_TILE - 1) / DC_TILE);
+            int cpg_eff = min(cpg, (n_keys + DC_MIN_KEYS - 1) / DC_MIN_KEYS);
             const int chunk = (((n_keys + cpg_eff - 1) / cpg_eff) + DC_TILE - 1) / DC_TILE * DC_TILE;   // whole tiles
             cpg_eff = (n_keys + chunk - 1) / chunk;                   // no empty ranges
             const bool active = in_grid && split < cpg_eff;
@@ -869,23 +867,36 @@ int tl_decode_chain(const tl_decode_job* jobs, int n_jobs, int M, void* sync_slo
     }
     (void)n_attn;
     constexpr int SMEM_CAP = 227 * 1024 - 1024;       // static shared memory of the kernel stays below 1 KB
-    static int DC_STAGE = 0;
-    if (!DC_STAGE) {
-        const char* e = getenv("TL_CHAIN_STAGE_KB");      // ring slot size: 16 (default) or 8 KB (more, smaller slots: all 8
-        DC_STAGE = (e && atoi(e) == 8) ? 8192 : 16384;    // consumer warps get a slot class of their own)
-    }
-    const int DC_KC = DC_STAGE / 4;
     const size_t xs_bytes = (((size_t)M * k_max * 2) + 127) & ~(size_t)127;
     const size_t attn_bytes = (size_t)DC_ATTN_BYTES;
     const size_t fixed = xs_bytes + attn_bytes + 2 * DC_MAX_STAGES * sizeof(uint64_t);
-    TL_REQUIRE(fixed + 4 * DC_STAGE <= (size_t)SMEM_CAP, TL_ERR_INVALID, "tl_decode_chain: M*K_max / context too large (%zu B fixed)", fixed);
-    int max_stages = (int)((SMEM_CAP - fixed) / DC_STAGE);
-    if (max_stages > DC_MAX_STAGES) max_stages = DC_MAX_STAGES;
-    int n_stages = 0, NW = 0;
-    for (int nw = DC_CW; nw >= 4; --nw) {
-        const int s = max_stages / nw * nw;
-        if (s > n_stages) { n_stages = s; NW = nw; }
+    // Ring geometry.  The consumers are the scarce resource (one warp per scheduler cannot hide its own latencies:
+    // measured 97 % busy at 5 warps), so all 8 consumer warps get a slot class of their own: 8 slots (n_stages % NW == 0:
+    // a slot is always drained by the same warp) as large as shared memory allows, capped at 24 KB.  TL_CHAIN_STAGE_KB
+    // forces a slot size (then as many slots as fit, NW = the largest divisor-compatible warp count).
+    static int forced_kb = -1;
+    if (forced_kb < 0) {
+        const char* e = getenv("TL_CHAIN_STAGE_KB");
+        forced_kb = e ? atoi(e) : 0;
     }
+    int DC_STAGE = 0, n_stages = 0, NW = 0;
+    TL_REQUIRE(fixed + 4 * 8192 <= (size_t)SMEM_CAP, TL_ERR_INVALID, "tl_decode_chain: M*K_max too large (%zu B fixed)", fixed);
+    if (!forced_kb) {
+        int kb = (int)((SMEM_CAP - fixed) / 8 / 1024);
+        if (kb > 24) kb = 24;
+        if (kb >= 12) { DC_STAGE = kb * 1024; n_stages = 8; NW = 8; }
+    }
+    if (!DC_STAGE) {
+        DC_STAGE = (forced_kb >= 8 ? forced_kb : 16) * 1024;
+        int max_stages = (int)((SMEM_CAP - fixed) / DC_STAGE);
+        if (max_stages > DC_MAX_STAGES) max_stages = DC_MAX_STAGES;
+        TL_REQUIRE(max_stages >= 4, TL_ERR_INVALID, "tl_decode_chain: fewer than 4 ring slots fit");
+        for (int nw = DC_CW; nw >= 4; --nw) {
+            const int st_ = max_stages / nw * nw;
+            if (st_ > n_stages) { n_stages = st_; NW = nw; }
+        }
+    }
+    const int DC_KC = (DC_STAGE / 4) & ~7;
     ChainParams prm = {};
     prm.n_jobs = n_jobs;
     prm.n_stages = n_stages;
@@ -895,8 +906,8 @@ int tl_decode_chain(const tl_decode_job* jobs, int n_jobs, int M, void* sync_slo
     if (dyn < 0) {
         const char* e = getenv("TL_CHAIN_DYNAMIC");      // 1: units handed out by ticket counters instead of the static split
         dyn = (e && e[0] == '1') ? 1 : 0;                // (measured worse: a ticket covers NW units, too coarse at the tail)
-        const char* a = getenv("TL_CHAIN_L2_AHEAD_KB");  // L2 prefetch lead per CTA
-        l2_ahead = a ? atoi(a) * 1024 : 192 * 1024;
+        const char* a = getenv("TL_CHAIN_L2_AHEAD_KB");  // L2 prefetch lead per CTA; off: measured 2.4x SLOWER at 192 KB
+        l2_ahead = a ? atoi(a) * 1024 : 0;               // (a prefetch followed closely by the load of the same lines is fetched twice)
         if (l2_ahead < 0) l2_ahead = 0;
     }
     prm.dynamic = dyn;

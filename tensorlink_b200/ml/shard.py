@@ -367,11 +367,14 @@ class CudaLayerGroup:
 
     # ------------------------------------------------------------------------------------------ chained decode step
     def chain_ok(self, B: int) -> bool:
-        """Rows / shapes the persistent chain kernel (csrc/decode_chain.cu) takes; TL_DECODE_IMPL=kernels forces the
-        per-kernel launch sequence."""
+        """Rows / shapes the persistent chain kernel (csrc/decode_chain.cu) takes.  Opt-in (TL_DECODE_IMPL=chain): measured
+        on Qwen2.5-7B it streams every Linear at the HBM rate (the GEMV phases of a layer sum to 69-75 us against a 72 us
+        bound) but pays 6-7 us per software dependency (release/acquire counter + restaging the input vector) where a
+        programmatic-dependent-launch boundary costs ~4 us: 323 tok/s against 355+ for the per-kernel sequence
+        (profiles/r02_decode_chain_timeline.txt)."""
         import os
         cfg = self.cfg
-        return (os.environ.get("TL_DECODE_IMPL", "chain") == "chain" and self.allow_chain and self.num_layers > 0
+        return (os.environ.get("TL_DECODE_IMPL", "kernels") == "chain" and self.allow_chain and self.num_layers > 0
                 and B <= min(4, gemv_max_rows()) and cfg.n_kv_heads * B <= 60 and cfg.n_heads // cfg.n_kv_heads <= 8
                 and cfg.head_dim in (64, 128))
 

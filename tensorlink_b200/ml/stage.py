@@ -141,6 +141,7 @@ class CudaStage:
             # warm up outside capture (first-use attribute setting, tensor-map cache), restoring the state it touches
             grp = self.slots[slot]
             saved = (grp.pos_dev.clone(), grp.kvlen_dev.clone(), self.ids_dec[slot].clone(), self.x_dec[slot].clone())
+            ctr_saved = self.sample_ctr.clone() if self.has_head else None      # the warm-up step must not consume a draw
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -148,6 +149,8 @@ class CudaStage:
             torch.cuda.current_stream().wait_stream(side)
             grp.pos_dev.copy_(saved[0]); grp.kvlen_dev.copy_(saved[1])
             self.ids_dec[slot].copy_(saved[2]); self.x_dec[slot].copy_(saved[3])
+            if ctr_saved is not None:
+                self.sample_ctr.copy_(ctr_saved)
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):

@@ -143,3 +143,31 @@ def test_generate_bounds_are_checked():
         w._handle_generate(full, synthetic_tokens(cfg, 1, 30).cuda(), max_new_tokens=8)      # 38 > max_seq: would write past the cache
     with pytest.raises(ValueError):
         w._handle_generate(full, synthetic_tokens(cfg, 2, 8).cuda(), max_new_tokens=4)       # 2 rows > max_batch
+
+
+def test_forward_and_backward_packets_through_the_torchnode_adapter():
+    """The reference's FORWARD / BACKWARD packets (p2p/torch_node.py:825-836, :865-869) in, reply packets out, over a real
+    stage: what a reference user process would exchange with a B200 worker."""
+    import pickle
+    from oracle import wire_oracle as W
+    from tensorlink_b200.ml.worker import DistributedWorker
+    from tensorlink_b200.p2p import torch_node as T
+    cfg = C.TINY_QWEN2
+    w = DistributedWorker(max_batch=2, max_seq=32)
+    mid = w.load_module({"module_id": "c" * 64, "name": cfg.name, "type": "offloaded_group", "layer_range": (0, 1), "training": True})
+    node = T.B200Torchnode(w)
+    x = (torch.randn(2, 8, cfg.hidden) * 0.1).bfloat16()
+    key = [0, 0, mid]
+    af = W.encode(())
+    request = T.build_forward(len(af).to_bytes(8, "big") + af + W.encode({"hidden_states": x, "use_cache": False}), key, mid)
+    reply = node.handle_data(request)
+    payload, module_id, rkey = T.parse_forward(reply)
+    out = W.decode(pickle.loads(payload))                                  # the reference user unpickles, then decodes the frame
+    assert module_id == mid and rkey == tuple(key) and out["use_cache"] is False
+    direct = w._handle_forward(mid, (9, 9, mid), {"hidden_states": x.cuda()})["hidden_states"].cpu()
+    assert torch.equal(out["hidden_states"], direct)
+    g = (torch.randn(2, 8, cfg.hidden) * 0.01).bfloat16()
+    back = node.handle_data(T.build_backward(W.encode(g), key))
+    gframe, tag = T.parse_backward(back)
+    want = w._handle_backward(mid, (9, 9, mid), g.cuda()).cpu()
+    assert tag == tuple(key) and torch.equal(W.decode(gframe), want)
