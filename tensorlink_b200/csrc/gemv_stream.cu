@@ -29,7 +29,7 @@ template <int M>
 __global__ void __launch_bounds__(GS_THREADS, 1)
 gemv_stream_kernel(const bf16* __restrict__ x, const bf16* __restrict__ W, bf16* __restrict__ y, int N, int K,
                    const bf16* __restrict__ bias, const bf16* __restrict__ residual, const bf16* __restrict__ norm_w,
-                   float eps, int flags, int P, int n_stages, int NW, int stage_bytes, int kc, const unsigned char* __restrict__ pf_ptr,
+                   float eps, int flags, int P, int n_stages, int NW, int stage_bytes, const unsigned char* __restrict__ pf_ptr,
                    unsigned long long pf_bytes) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* ring = smem;                                                    // [n_stages][stage_bytes]
@@ -48,8 +48,8 @@ gemv_stream_kernel(const bf16* __restrict__ x, const bf16* __restrict__ W, bf16*
     // NW consumer warps take units; n_stages %% NW == 0, so ring slot s is ALWAYS consumed by warp s %% NW and every
     // waiter observes every phase of the barriers it waits on (no mbarrier parity aliasing).
     const int n_groups = (n_units + NW - 1) / NW;
-    const bool chunked = kc < K;                                       // a pair does not fit one stage
-    const int KC = chunked ? kc : K;
+    const bool chunked = K > GS_KC || (size_t)K * 4 > GS_STAGE_BYTES;  // a pair does not fit one stage
+    const int KC = chunked ? GS_KC : K;
     const int n_chunks = (K + KC - 1) / KC;
 
     if (tid == 0) {
@@ -110,18 +110,8 @@ gemv_stream_kernel(const bf16* __restrict__ x, const bf16* __restrict__ W, bf16*
         // ================================================================= consumers
         // x / residual are produced by the previous kernel: wait for it (no-op without the PDL launch attribute);
         // the producer warp above streams weights, which nobody writes, without waiting.
-        // the norm gain is a weight: fetch this thread's slice BEFORE waiting for the previous kernel (its round trip then
-        // overlaps the wait instead of following it)
-        const int nvec = K >> 3;
-        constexpr int GW = 4;                                   // gain vectors a thread can hold (K <= 8192)
-        uint4 gw[GW];
-        const bool gw_ok = norm_w && nvec <= GW * GS_CONSUMER_WARPS * 32;
-        if (gw_ok) {
-#pragma unroll
-            for (int t = 0; t < GW; ++t)
-                if (tid + t * GS_CONSUMER_WARPS * 32 < nvec) gw[t] = reinterpret_cast<const uint4*>(norm_w)[tid + t * GS_CONSUMER_WARPS * 32];
-        }
         asm volatile("griddepcontrol.wait;" ::: "memory");
+        const int nvec = K >> 3;
         if (norm_w) {
             float ss[M];
 #pragma unroll
@@ -152,17 +142,8 @@ gemv_stream_kernel(const bf16* __restrict__ x, const bf16* __restrict__ W, bf16*
                 for (int w = 0; w < GS_CONSUMER_WARPS; ++w) t += s_part[w][m];
                 rstd[m] = 1.0f / sqrtf(t / (float)K + eps);
             }
-            int gi = 0;
-            for (int v = tid; v < nvec; v += GS_CONSUMER_WARPS * 32, ++gi) {
-                uint4 g;
-                if (gw_ok) {
-                    g = gw[0];
-#pragma unroll
-                    for (int t = 1; t < GW; ++t)
-                        if (gi == t) g = gw[t];
-                } else {
-                    g = reinterpret_cast<const uint4*>(norm_w)[v];
-                }
+            for (int v = tid; v < nvec; v += GS_CONSUMER_WARPS * 32) {
+                const uint4 g = reinterpret_cast<const uint4*>(norm_w)[v];
                 const uint32_t* g32 = reinterpret_cast<const uint32_t*>(&g);
 #pragma unroll
                 for (int m = 0; m < M; ++m) {
@@ -186,35 +167,15 @@ gemv_stream_kernel(const bf16* __restrict__ x, const bf16* __restrict__ W, bf16*
         const bool swiglu = flags & TL_EPI_SWIGLU;
         const int n_out = swiglu ? npairs : N;
         // epilogue for one finished pair (all lanes hold the reduced sums)
-        // bias / residual of a pair are fetched by lane 0 BEFORE the dot product (their round trip would otherwise sit
-        // between the last FMA and the store of every unit)
-        auto preload = [&](int pair, float (&bs)[2], float (&rs)[M][2]) {
-            bs[0] = bs[1] = 0.f;
-#pragma unroll
-            for (int m = 0; m < M; ++m) rs[m][0] = rs[m][1] = 0.f;
-            if (lane != 0) return;
-            const int r0 = 2 * pair;
-            if (flags & TL_EPI_BIAS) {
-                bs[0] = bf2f(bias[r0]);
-                bs[1] = bf2f(bias[r0 + 1]);
-            }
-            if (flags & TL_EPI_RESIDUAL) {
-#pragma unroll
-                for (int m = 0; m < M; ++m) {
-                    rs[m][0] = bf2f(residual[(size_t)m * N + r0]);
-                    rs[m][1] = bf2f(residual[(size_t)m * N + r0 + 1]);
-                }
-            }
-        };
-        auto finish = [&](int pair, const float (&a0)[M], const float (&a1)[M], const float (&bs)[2], const float (&rs)[M][2]) {
+        auto finish = [&](int pair, const float (&a0)[M], const float (&a1)[M]) {
             if (lane != 0) return;
             const int r0 = 2 * pair;
 #pragma unroll
             for (int m = 0; m < M; ++m) {
                 float v0 = a0[m], v1 = a1[m];
                 if (flags & TL_EPI_BIAS) {
-                    v0 += bs[0];
-                    v1 += bs[1];
+                    v0 += bf2f(bias[r0]);
+                    v1 += bf2f(bias[r0 + 1]);
                 }
                 if (swiglu) {
                     const float gate = rbf(v0), up = rbf(v1);
@@ -222,8 +183,8 @@ gemv_stream_kernel(const bf16* __restrict__ x, const bf16* __restrict__ W, bf16*
                 } else {
                     float t0 = rbf(v0), t1 = rbf(v1);
                     if (flags & TL_EPI_RESIDUAL) {
-                        t0 += rs[m][0];
-                        t1 += rs[m][1];
+                        t0 += bf2f(residual[(size_t)m * N + r0]);
+                        t1 += bf2f(residual[(size_t)m * N + r0 + 1]);
                     }
                     *reinterpret_cast<uint32_t*>(y + (size_t)m * N + r0) = pack_bf16(t0, t1);
                 }
@@ -258,10 +219,8 @@ gemv_stream_kernel(const bf16* __restrict__ x, const bf16* __restrict__ W, bf16*
             const bool valid = unit < n_units;
             const int pair0 = p_begin + unit * P;
             float a0[M], a1[M];
-            float bs[2], rs[M][2];
 #pragma unroll
             for (int m = 0; m < M; ++m) a0[m] = a1[m] = 0.f;
-            if (valid) preload(pair0, bs, rs);
             for (int c = 0; c < n_chunks; ++c, seq += NW) {
                 const int stage = seq % n_stages;
                 const uint32_t phase = (uint32_t)(seq / n_stages) & 1u;
@@ -272,20 +231,13 @@ gemv_stream_kernel(const bf16* __restrict__ x, const bf16* __restrict__ W, bf16*
                         const int np = min(P, p_end - pair0);
                         for (int pp = 0; pp < np; ++pp) {
                             float b0[M], b1[M];
-                            float bn[2], rn[M][2];
 #pragma unroll
                             for (int m = 0; m < M; ++m) b0[m] = b1[m] = 0.f;
-                            if (pp + 1 < np) preload(pair0 + pp + 1, bn, rn);      // next pair's, under this pair's FMAs
                             dot2(reinterpret_cast<const uint4*>(src + (size_t)(2 * pp) * K * 2),
                                  reinterpret_cast<const uint4*>(src + (size_t)(2 * pp + 1) * K * 2), 0, nvec, b0, b1);
 #pragma unroll
                             for (int m = 0; m < M; ++m) { b0[m] = warp_sum(b0[m]); b1[m] = warp_sum(b1[m]); }
-                            finish(pair0 + pp, b0, b1, bs, rs);
-                            if (pp + 1 < np) {
-                                bs[0] = bn[0]; bs[1] = bn[1];
-#pragma unroll
-                                for (int m = 0; m < M; ++m) { rs[m][0] = rn[m][0]; rs[m][1] = rn[m][1]; }
-                            }
+                            finish(pair0 + pp, b0, b1);
                         }
                     } else {
                         const int k0 = c * KC;
@@ -299,7 +251,7 @@ gemv_stream_kernel(const bf16* __restrict__ x, const bf16* __restrict__ W, bf16*
             if (valid && chunked) {
 #pragma unroll
                 for (int m = 0; m < M; ++m) { a0[m] = warp_sum(a0[m]); a1[m] = warp_sum(a1[m]); }
-                finish(pair0, a0, a1, bs, rs);
+                finish(pair0, a0, a1);
             }
         }
     }
@@ -333,40 +285,20 @@ static int launch_stream(const void* x, const void* W, void* y, int N, int K, co
     }
     const size_t xs_bytes = (((size_t)M * K * 2) + 15) & ~(size_t)15;
     const size_t fixed = xs_bytes + 2 * GS_MAX_STAGES * sizeof(uint64_t);
-    bool chunked = K > GS_KC || (size_t)K * 4 > GS_STAGE_BYTES;
+    const bool chunked = K > GS_KC || (size_t)K * 4 > GS_STAGE_BYTES;
     int P = chunked ? 1 : (int)(GS_STAGE_BYTES / ((size_t)K * 4));
     if (P < 1) P = 1;
     if (P > 8) P = 8;
-    int stage_bytes, n_stages = 0, NW = 0, kc = K;
-    // TL_GEMV_WIDE=0 restores the round-1 geometry of the K-chunked case (16 KB slots, 10 slots, 5 consumer warps)
-    static int wide = -1;
-    if (wide < 0) {
-        const char* e = getenv("TL_GEMV_WIDE");
-        wide = (e && e[0] == '0') ? 0 : 1;
-    }
-    const int wide_kb = (int)(((size_t)SMEM_CAP > fixed ? (size_t)SMEM_CAP - fixed : 0) / GS_CONSUMER_WARPS / 1024);
-    if (chunked && wide && per_sm == 1 && wide_kb >= 12) {
-        // K-chunked rows (K > 4096, e.g. the down projection): measured with device-side cycle counters, 5 consumer warps
-        // (one per scheduler) are ~97 % busy and the producer waits for free slots 40 % of the time: the consumers, not
-        // HBM, set the pace.  So: one slot class per consumer warp, 8 slots as large as shared memory allows (<= 24 KB).
-        stage_bytes = (wide_kb > 24 ? 24 : wide_kb) * 1024;
-        kc = (stage_bytes / 4) & ~7;
-        n_stages = GS_CONSUMER_WARPS;
-        NW = GS_CONSUMER_WARPS;
-        chunked = kc < K;
-        if (!chunked) { kc = K; }
-    } else {
-        if (chunked) kc = GS_KC;
-        // a stage holds exactly one unit: P whole pairs, or one 4096-column chunk of one pair
-        stage_bytes = chunked ? GS_STAGE_BYTES : (int)((((size_t)P * K * 4) + 127) & ~(size_t)127);
-        int max_stages = (int)((SMEM_CAP - fixed) / stage_bytes);
-        if (max_stages > GS_MAX_STAGES) max_stages = GS_MAX_STAGES;
-        if (max_stages < 4) return 1;   // caller falls back to the register-streaming kernel
-        // pick (n_stages, NW): n_stages a multiple of NW, as many bytes in flight as possible, then as many warps
-        for (int nw = GS_CONSUMER_WARPS; nw >= 4; --nw) {
-            const int st_ = max_stages / nw * nw;
-            if (st_ > n_stages) { n_stages = st_; NW = nw; }
-        }
+    // a stage holds exactly one unit: P whole pairs, or one 4096-column chunk of one pair
+    const int stage_bytes = chunked ? GS_STAGE_BYTES : (int)((((size_t)P * K * 4) + 127) & ~(size_t)127);
+    int max_stages = (int)((SMEM_CAP - fixed) / stage_bytes);
+    if (max_stages > GS_MAX_STAGES) max_stages = GS_MAX_STAGES;
+    if (max_stages < 4) return 1;   // caller falls back to the register-streaming kernel
+    // pick (n_stages, NW): n_stages a multiple of NW, as many bytes in flight as possible, then as many warps
+    int n_stages = 0, NW = 0;
+    for (int nw = GS_CONSUMER_WARPS; nw >= 4; --nw) {
+        const int st_ = max_stages / nw * nw;
+        if (st_ > n_stages) { n_stages = st_; NW = nw; }
     }
     const size_t smem = (size_t)n_stages * stage_bytes + fixed;
     const int npairs = N >> 1;
@@ -388,7 +320,7 @@ static int launch_stream(const void* x, const void* W, void* y, int N, int K, co
     cfg.attrs = attr;
     cfg.numAttrs = use_pdl ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kern, (const bf16*)x, (const bf16*)W, (bf16*)y, N, K, (const bf16*)bias, (const bf16*)residual,
-                       (const bf16*)norm_w, eps, flags, P, n_stages, NW, stage_bytes, kc, (const unsigned char*)pf_ptr,
+                       (const bf16*)norm_w, eps, flags, P, n_stages, NW, stage_bytes, (const unsigned char*)pf_ptr,
                        (unsigned long long)(pf_bytes & ~(size_t)15));
     return check_launch("tl_gemv_bf16/stream");
 }

@@ -351,8 +351,8 @@ class CudaLayerGroup:
         w = self._dbufs(B)
         if advance:
             nat.advance_pos(self.kvlen_dev, None, 1)
-        if self.chain_ok(B):
-            self._decode_step_chained(x, B, out)
+        if self.chain_ok(B) or self.dq_ok(B):
+            (self._decode_step_chained if self.chain_ok(B) else self._decode_step_dq)(x, B, out)
             if advance:
                 nat.advance_pos(self.pos_dev, None, 1)
             return
@@ -433,6 +433,44 @@ class CudaLayerGroup:
                  next_w=v[f"l{l0}.wo"])
         for ch in self._decode_chains(x, B, out):
             ch.launch()
+
+    def dq_ok(self, B: int) -> bool:
+        """TL_DECODE_IMPL=dq: the per-kernel sequence, except that the down projection of layer j and the qkv projection
+        of layer j+1 run as ONE two-job chain launch (one software dependency instead of a launch boundary between a
+        long and a short weight stream)."""
+        import os
+        return os.environ.get("TL_DECODE_IMPL", "kernels") == "dq" and self.allow_chain and self.num_layers > 1 and B <= min(4, gemv_max_rows())
+
+    def _decode_step_dq(self, x: torch.Tensor, B: int, out: Optional[torch.Tensor]):
+        cfg, v = self.cfg, self.p.v
+        w = self._dbufs(B)
+        key = ("dq", B, x.data_ptr(), 0 if out is None else out.data_ptr())
+        if key not in self._chains:
+            J = nat.make_job
+            if self.chain_sync is None:
+                self.chain_sync = torch.zeros(self.num_layers + 1, nat.CHAIN_SYNC_BYTES // 4, dtype=torch.int32, device=self.device)
+                self.chain_attn_ws = torch.empty(nat.decode_chain_ws(min(self.B_max, 4), cfg.n_heads, cfg.n_kv_heads, cfg.head_dim),
+                                                 dtype=torch.uint8, device=self.device)
+            launches = []
+            for j in range(self.num_layers - 1):
+                li, ln = self.layer_ids[j], self.layer_ids[j + 1]
+                bq = v.get(f"l{ln}.bqkv")
+                jobs = [J(nat.JOB_GEMV, N=cfg.hidden, K=cfg.intermediate, flags=nat.EPI_RESIDUAL, W=v[f"l{li}.wd"], x=w.act, y=x, residual=x),
+                        J(nat.JOB_GEMV, N=cfg.qkv_dim, K=cfg.hidden, flags=nat.EPI_BIAS if bq is not None else 0, W=v[f"l{ln}.wqkv"], x=x,
+                          y=w.qkv, bias=bq, norm_w=v[f"l{ln}.ln1"], eps=cfg.rms_eps)]
+                launches.append(nat.DecodeChain(jobs, B, self.chain_sync[j], self.chain_attn_ws, v[f"l{ln}.wo"]))
+            self._chains[key] = launches
+        chains = self._chains[key]
+        l0 = self.layer_ids[0]
+        nat.gemv(x, v[f"l{l0}.wqkv"], out=w.qkv, bias=v.get(f"l{l0}.bqkv"), norm_w=v[f"l{l0}.ln1"], eps=cfg.rms_eps, next_w=v[f"l{l0}.wo"])
+        for j, li in enumerate(self.layer_ids):
+            self._decode_attention(j, li, B, w)
+            nat.gemv(w.attn, v[f"l{li}.wo"], out=x, residual=x, next_w=v[f"l{li}.wgu"])
+            nat.gemv(x, v[f"l{li}.wgu"], out=w.act, norm_w=v[f"l{li}.ln2"], eps=cfg.rms_eps, flags=nat.EPI_SWIGLU, next_w=v[f"l{li}.wd"])
+            if j + 1 < self.num_layers:
+                chains[j].launch()
+            else:
+                nat.gemv(w.act, v[f"l{li}.wd"], out=x if out is None else out, residual=x, next_w=self.weights_after_last_layer)
 
     def n_chain_launches(self) -> int:
         per = self._chain_group()

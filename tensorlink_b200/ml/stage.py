@@ -169,6 +169,9 @@ class CudaStage:
         gemv = B <= gemv_max_rows()
         if self.slots[0].chain_ok(B):
             n = self.slots[0].n_chain_launches() + 2       # qkv of the first layer + one persistent launch per layer group
+        elif self.slots[0].dq_ok(B):
+            # first qkv + per layer: attention (1 fused / 3), o, gate/up, [down + next qkv] as one chain launch
+            n = 1 + len(self.slots[0].layer_ids) * (3 + (1 if fused else 3)) + 2
         else:
             # GEMV path: 4 Linears + attention (1 fused / 3); batched: 4 GEMMs + 3 split-K reduce(+norm) passes + attention
             n = len(self.slots[0].layer_ids) * ((7 if gemv else 10) - (2 if fused else 0)) + 2 + (0 if gemv else 1)
