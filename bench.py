@@ -629,6 +629,10 @@ def main():
     # ---- pipeline occupancy: fraction of the decode phase this rank's compute stream spent inside decode launches
     # (the rest = waiting for a neighbour's activations / ids, i.e. exposed transfer + pipeline bubble)
     dm.generate(ids_dev, max_new_tokens=new, profile=True)
+    decode_span = torch.tensor([dm.timers["decode_span_s"]], device=dm.device)
+    if world > 1:
+        dist.all_reduce(decode_span, op=dist.ReduceOp.MAX)
+    decode_span = float(decode_span)
     busy = torch.tensor([dm.timers["decode_busy_s"] / max(dm.timers["decode_span_s"], 1e-9)], device=dm.device)
     busy_min, busy_max = busy.clone(), busy.clone()
     if world > 1:
@@ -674,6 +678,11 @@ def main():
                            "achieved_GBps_whole_generate": step_bytes * passes / t_dev / 1e9,
                            "frac_of_hbm_peak_whole_generate": step_bytes * passes / t_dev / 1e9 / hbm_peak,
                            "hbm_bound_tokens_per_s": rows / ideal_s,
+                           # the decode phase alone (CUDA events around the token loop of one extra generate): long prompts
+                           # make the whole-generate figure mostly a prefill (tensor-core) number
+                           "decode_only": {"tokens_per_s": rows * (new - 1) / decode_span, "ms_per_token_step": decode_span / (new - 1) * 1e3,
+                                           "frac_of_hbm_bound": rows * (new - 1) / decode_span / (rows / ideal_s),
+                                           "prefill_s": max(t_dev / args.steps - decode_span, 0.0)},
                            "note": "whole timed region incl. prefill, attention, launch gaps and pipeline bubbles"}
     ring = getattr(dm, "_ring", None) is not None
     launches = args.steps * (new - 1) * N * dm.stage.n_decode_launches(args.rows_per_gpu, ring=ring)

@@ -159,7 +159,14 @@ def _p(t: Optional[torch.Tensor]) -> Optional[int]:
     return t.data_ptr()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream() -> int:
+    """The current CUDA stream of the current device as a raw handle (every launch asks: the C accessor costs ~0.1 us,
+    ``torch.cuda.current_stream().cuda_stream`` builds a Python Stream object each time)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 

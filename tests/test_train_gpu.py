@@ -277,3 +277,32 @@ def test_deferred_weight_gradients_equal_per_micro_batch_accumulation():
     assert abs(out[1][0] - out[4][0]) < 2e-3
     for k, v in out[1][1].items():
         assert O.rel_l2(out[4][1][k], v) <= 6e-3, k
+
+
+def test_other_optimizer_classes_step_like_torch():
+    """``optimizer=torch.optim.SGD`` (any Optimizer subclass, like the reference's worker accepts, ml/worker.py:1309-1327):
+    the class's own step runs on the device over the flat arena; the update equals lr * (momentum-filtered) gradient."""
+    from tensorlink_b200.ml import DistributedModel
+    cfg = C.TINY_QWEN2_D128
+    ids = synthetic_tokens(cfg, 2, 24)
+    dm = DistributedModel(cfg, training=True, max_batch=2, max_seq=32, optimizer=torch.optim.SGD)
+    opt = dm.create_optimizer(lr=0.5, momentum=0.0)
+    opt.zero_grad()
+    out = dm(ids, labels=ids)
+    out.loss.backward()
+    p = dm.stage.params
+    p.grad_settle()
+    before, g = p.flat.float().clone(), p.grad.float().clone()
+    opt.step()
+    want = (before - 0.5 * g).bfloat16().float()
+    assert O.rel_l2(p.flat.float(), want) <= 1e-3 and float((p.flat.float() - before).abs().sum()) > 0
+    losses = [float(out.loss)]
+    for _ in range(5):
+        opt.zero_grad()
+        o = dm(ids, labels=ids)
+        o.loss.backward()
+        opt.step()
+        losses.append(float(o.loss))
+    assert losses[-1] < losses[0]
+    with pytest.raises(TypeError):
+        DistributedModel(cfg, training=True, max_batch=2, max_seq=32, optimizer="sgd").create_optimizer(lr=0.1)
