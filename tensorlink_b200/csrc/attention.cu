@@ -342,6 +342,173 @@ __global__ void __launch_bounds__(DEC_THREADS) attn_decode_split_kernel(const bf
     }
 }
 
+// ---- split phase on tensor cores (mma.sync m16n8k16).  The n_rep query heads that share a kv head are the M rows of
+// the MMA (16 rows, the unused ones zero): per cached key the CUDA-core kernel above spends 2 * n_rep * D FMAs plus the
+// bf16 unpacking, which at n_rep = 7 is more issue bandwidth than an SM has at its share of the HBM rate (ncu, round 2:
+// 56 us per layer for 67 MB of KV at B = 32, T = 1026 = 1.2 TB/s).  Here a CTA stages its DEC_CHUNK keys and values in
+// shared memory with cp.async (coalesced 16-byte pieces, the second 64-key tile in flight while the first is used), each
+// of the 4 warps owns 16 keys of every 64-key tile with its own online-softmax state, and the 4 states are merged
+// through shared memory into the (m, l, o) record the reduce kernel below expects.
+template <int D>
+__global__ void __launch_bounds__(FA_THREADS) attn_decode_mma_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k_cache,
+                                                                      const bf16* __restrict__ v_cache, float* __restrict__ ws,
+                                                                      const int32_t* __restrict__ kv_len_dev, int n_h, int n_kv,
+                                                                      int T_max, int n_splits, float scale_log2) {
+    constexpr int LDS = D + 8;
+    constexpr int CPR = D / 8;
+    constexpr int NT = DEC_CHUNK / FA_BKV;                 // 64-key tiles per CTA
+    const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
+    const int kv_len = *kv_len_dev;
+    const int c0 = split * DEC_CHUNK;
+    if (c0 >= kv_len) return;
+    const int n_rep = n_h / n_kv;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    bf16* sQ = reinterpret_cast<bf16*>(smem_raw);          // [16][LDS]
+    bf16* sK = sQ + 16 * LDS;                              // [NT][64][LDS]
+    bf16* sV = sK + NT * FA_BKV * LDS;                     // [NT][64][LDS]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const bf16* kg = k_cache + ((size_t)b * n_kv + kvh) * T_max * D;
+    const bf16* vg = v_cache + ((size_t)b * n_kv + kvh) * T_max * D;
+    const bf16* qg = q + ((size_t)b * n_h + kvh * n_rep) * D;
+    for (int c = tid; c < 16 * CPR; c += FA_THREADS) {
+        const int r = c / CPR, cc = c - r * CPR;
+        cp_async16(sQ + r * LDS + cc * 8, qg + (size_t)(r < n_rep ? r : 0) * D + cc * 8, r < n_rep);
+    }
+    const int n_tiles = min(NT, (kv_len - c0 + FA_BKV - 1) / FA_BKV);
+    for (int t = 0; t < n_tiles; ++t) {
+        const int kv0 = c0 + t * FA_BKV;
+        for (int c = tid; c < FA_BKV * CPR; c += FA_THREADS) {
+            const int r = c / CPR, cc = c - r * CPR;
+            const bool ok = (kv0 + r) < kv_len;
+            const size_t off = (size_t)(ok ? kv0 + r : 0) * D + cc * 8;
+            cp_async16(sK + (t * FA_BKV + r) * LDS + cc * 8, kg + off, ok);
+            cp_async16(sV + (t * FA_BKV + r) * LDS + cc * 8, vg + off, ok);
+        }
+        cp_async_commit();                                  // (the q rows ride in the first group)
+    }
+    float o[D / 8][4];
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+    uint32_t qf[D / 16][4];
+    for (int t = 0; t < n_tiles; ++t) {
+        if (t == 0 && n_tiles > 1) cp_async_wait<1>(); else cp_async_wait<0>();
+        __syncthreads();
+        if (t == 0) {
+#pragma unroll
+            for (int ks = 0; ks < D / 16; ++ks)
+                ldmatrix_x4(qf[ks], sQ + (lane & 15) * LDS + ks * 16 + (lane >> 4) * 8);
+        }
+        const bf16* sKb = sK + (t * FA_BKV + warp * 16) * LDS;     // this warp's 16 keys of the tile
+        const bf16* sVb = sV + (t * FA_BKV + warp * 16) * LDS;
+        float sc[2][4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) sc[i][0] = sc[i][1] = sc[i][2] = sc[i][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < D / 16; ++ks) {
+            uint32_t bfr[4];
+            const int mi = lane >> 3;
+            ldmatrix_x4(bfr, sKb + ((mi >> 1) * 8 + (lane & 7)) * LDS + ks * 16 + (mi & 1) * 8);
+            mma_bf16_16816(sc[0], qf[ks], bfr[0], bfr[1]);
+            mma_bf16_16816(sc[1], qf[ks], bfr[2], bfr[3]);
+        }
+        const int key0 = c0 + t * FA_BKV + warp * 16;
+        float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int key = key0 + i * 8 + 2 * t4 + (e & 1);
+                const float v = key < kv_len ? sc[i][e] * scale_log2 : -INFINITY;
+                sc[i][e] = v;
+                mx[e >> 1] = fmaxf(mx[e >> 1], v);
+            }
+        float alpha[2], msub[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+            const float m_new = fmaxf(m_run[r], mx[r]);
+            msub[r] = (m_new == -INFINITY) ? 0.f : m_new;
+            alpha[r] = exp2f(m_run[r] - msub[r]);
+            m_run[r] = m_new;
+        }
+        float rs[2] = {0.f, 0.f};
+        uint32_t pf[4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float p0 = exp2f(sc[i][0] - msub[0]), p1 = exp2f(sc[i][1] - msub[0]);
+            const float p2 = exp2f(sc[i][2] - msub[1]), p3 = exp2f(sc[i][3] - msub[1]);
+            rs[0] += p0 + p1;
+            rs[1] += p2 + p3;
+            pf[i * 2] = pack_bf16(p0, p1);                  // P is cast to bf16 before P.V (SDPA contract); l keeps fp32
+            pf[i * 2 + 1] = pack_bf16(p2, p3);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 1);
+            rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 2);
+            l_run[r] = l_run[r] * alpha[r] + rs[r];
+        }
+#pragma unroll
+        for (int i = 0; i < D / 8; ++i) {
+            o[i][0] *= alpha[0];
+            o[i][1] *= alpha[0];
+            o[i][2] *= alpha[1];
+            o[i][3] *= alpha[1];
+        }
+#pragma unroll
+        for (int dp = 0; dp < D / 16; ++dp) {
+            uint32_t bfr[4];
+            const int mi = lane >> 3;
+            ldmatrix_x4_trans(bfr, sVb + ((mi & 1) * 8 + (lane & 7)) * LDS + dp * 16 + (mi >> 1) * 8);
+            mma_bf16_16816(o[2 * dp], pf, bfr[0], bfr[1]);
+            mma_bf16_16816(o[2 * dp + 1], pf, bfr[2], bfr[3]);
+        }
+    }
+    // ---- merge the 4 warps' states (rows g and g+8 of each thread) through shared memory; only rows < n_rep matter
+    __syncthreads();                                        // everyone is done with the K / V tiles
+    float* sM = reinterpret_cast<float*>(sK);               // [4][16]
+    float* sL = sM + 64;                                    // [4][16]
+    float* sO = sL + 64;                                    // [4][16][D]
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int row = g + r * 8;
+        if (t4 == 0) { sM[warp * 16 + row] = m_run[r]; sL[warp * 16 + row] = l_run[r]; }
+#pragma unroll
+        for (int i = 0; i < D / 8; ++i) {
+            sO[(warp * 16 + row) * D + i * 8 + 2 * t4] = o[i][2 * r];
+            sO[(warp * 16 + row) * D + i * 8 + 2 * t4 + 1] = o[i][2 * r + 1];
+        }
+    }
+    __syncthreads();
+    float* rec = ws + (((size_t)b * n_kv + kvh) * n_splits + split) * dec_rec_floats(n_rep, D);
+    for (int i = tid; i < n_rep * D; i += FA_THREADS) {
+        const int r = i / D, dd = i - r * D;
+        const float m = fmaxf(fmaxf(sM[r], sM[16 + r]), fmaxf(sM[32 + r], sM[48 + r]));
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const float mw = sM[w * 16 + r];
+            if (mw != -INFINITY) v += sO[(w * 16 + r) * D + dd] * exp2f(mw - m);
+        }
+        rec[2 * n_rep + i] = v;
+    }
+    if (tid < n_rep) {
+        const int r = tid;
+        const float m = fmaxf(fmaxf(sM[r], sM[16 + r]), fmaxf(sM[32 + r], sM[48 + r]));
+        float l = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const float mw = sM[w * 16 + r];
+            if (mw != -INFINITY) l += sL[w * 16 + r] * exp2f(mw - m);
+        }
+        rec[r] = m;
+        rec[n_rep + r] = l;
+    }
+}
+
 template <int D>
 __global__ void attn_decode_reduce_kernel(const float* __restrict__ ws, bf16* __restrict__ out,
                                           const int32_t* __restrict__ kv_len_dev, int n_h, int n_kv, int n_splits) {
@@ -433,6 +600,25 @@ int tl_attn_decode_fwd(const void* q, const void* k_cache, const void* v_cache, 
     const float sl2 = scale * 1.4426950408889634f;
     cudaStream_t st = (cudaStream_t)stream;
     const dim3 g1(n_splits, n_kv, B), g2(n_h, B);
+    // split phase on tensor cores (attn_decode_mma_kernel) unless TL_DECODE_ATTN=simt asks for the CUDA-core kernel
+    const char* impl = getenv("TL_DECODE_ATTN");
+    if (!(impl && impl[0] == 's')) {
+        const size_t smem = (size_t)(16 + 2 * DEC_CHUNK) * (d + 8) * sizeof(bf16);
+        if (d == 64) {
+            static bool done = false;
+            if (!done) { cudaFuncSetAttribute(attn_decode_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); done = true; }
+            attn_decode_mma_kernel<64><<<g1, FA_THREADS, smem, st>>>((const bf16*)q, (const bf16*)k_cache, (const bf16*)v_cache,
+                                                                    (float*)workspace, kv_len_dev, n_h, n_kv, T_max, n_splits, sl2);
+            attn_decode_reduce_kernel<64><<<g2, 64, 0, st>>>((const float*)workspace, (bf16*)out, kv_len_dev, n_h, n_kv, n_splits);
+        } else {
+            static bool done = false;
+            if (!done) { cudaFuncSetAttribute(attn_decode_mma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); done = true; }
+            attn_decode_mma_kernel<128><<<g1, FA_THREADS, smem, st>>>((const bf16*)q, (const bf16*)k_cache, (const bf16*)v_cache,
+                                                                     (float*)workspace, kv_len_dev, n_h, n_kv, T_max, n_splits, sl2);
+            attn_decode_reduce_kernel<128><<<g2, 128, 0, st>>>((const float*)workspace, (bf16*)out, kv_len_dev, n_h, n_kv, n_splits);
+        }
+        return check_launch("tl_attn_decode_fwd");
+    }
     if (d == 64) {
         attn_decode_split_kernel<64><<<g1, DEC_THREADS, 0, st>>>((const bf16*)q, (const bf16*)k_cache, (const bf16*)v_cache,
                                                                   (float*)workspace, kv_len_dev, n_h, n_kv, T_max, n_splits, sl2);

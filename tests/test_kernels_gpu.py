@@ -295,8 +295,13 @@ def test_attn_prefill(nat, monkeypatch, impl, B, S, past, n_h, n_kv, d):
 
 
 @pytest.mark.parametrize("B,kv_len,n_h,n_kv,d", [(1, 1, 14, 2, 64), (2, 127, 4, 2, 128), (1, 128, 28, 4, 128),
-                                                 (3, 129, 8, 8, 64), (1, 1000, 28, 4, 128), (2, 2048, 32, 8, 128)])
-def test_attn_decode(nat, B, kv_len, n_h, n_kv, d):
+                                                 (3, 129, 8, 8, 64), (1, 1000, 28, 4, 128), (2, 2048, 32, 8, 128),
+                                                 (32, 4096, 28, 4, 128), (4, 65, 16, 2, 128), (5, 193, 28, 4, 128)])
+@pytest.mark.parametrize("impl", ["mma", "simt"])
+def test_attn_decode(nat, B, kv_len, n_h, n_kv, d, impl, monkeypatch):
+    """split-KV decode attention: the tensor-core split kernel (default: the GQA group's query heads are the MMA's M rows)
+    and the CUDA-core one (TL_DECODE_ATTN=simt) against the oracle."""
+    monkeypatch.setenv("TL_DECODE_ATTN", impl)
     q, k, v, ref, f32 = _attn_case(B, 1, kv_len - 1, n_h, n_kv, d, seed=40)
     T_max = kv_len + 100
     kc = torch.zeros(B, n_kv, T_max, d, dtype=torch.bfloat16)
