@@ -195,6 +195,7 @@ __global__ void __launch_bounds__(FA_THREADS) attn_prefill_kernel(const bf16* __
 
 // ================================================================================================ decode
 constexpr int DEC_CHUNK = 128, DEC_THREADS = 128, DEC_MAX_REP = 8;
+constexpr int DEC_CHUNK_MMA = 256;      // keys per CTA of the tensor-core split kernel (four 64-key tiles through a 2-tile ring)
 
 // partial record per (b, kv head, split): m[REP], l[REP], o[REP][D]  (fp32)
 __host__ __device__ inline size_t dec_rec_floats(int n_rep, int D) { return (size_t)n_rep * (2 + D); }
@@ -346,8 +347,8 @@ __global__ void __launch_bounds__(DEC_THREADS) attn_decode_split_kernel(const bf
 // the MMA (16 rows, the unused ones zero): per cached key the CUDA-core kernel above spends 2 * n_rep * D FMAs plus the
 // bf16 unpacking, which at n_rep = 7 is more issue bandwidth than an SM has at its share of the HBM rate (ncu, round 2:
 // 56 us per layer for 67 MB of KV at B = 32, T = 1026 = 1.2 TB/s).  Here a CTA stages its DEC_CHUNK keys and values in
-// shared memory with cp.async (coalesced 16-byte pieces, the second 64-key tile in flight while the first is used), each
-// of the 4 warps owns 16 keys of every 64-key tile with its own online-softmax state, and the 4 states are merged
+// shared memory with cp.async (coalesced 16-byte pieces, a ring of two 64-key tiles: the next tile is in flight while one
+// is used; DEC_CHUNK_MMA = 256 keys per CTA), each of the 4 warps owns 16 keys of every 64-key tile with its own online-softmax state, and the 4 states are merged
 // through shared memory into the (m, l, o) record the reduce kernel below expects.
 template <int D>
 __global__ void __launch_bounds__(FA_THREADS) attn_decode_mma_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k_cache,
@@ -356,10 +357,10 @@ __global__ void __launch_bounds__(FA_THREADS) attn_decode_mma_kernel(const bf16*
                                                                       int T_max, int n_splits, float scale_log2) {
     constexpr int LDS = D + 8;
     constexpr int CPR = D / 8;
-    constexpr int NT = DEC_CHUNK / FA_BKV;                 // 64-key tiles per CTA
+    constexpr int NT = 2;                                  // shared-memory ring: two 64-key tiles
     const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
     const int kv_len = *kv_len_dev;
-    const int c0 = split * DEC_CHUNK;
+    const int c0 = split * DEC_CHUNK_MMA;
     if (c0 >= kv_len) return;
     const int n_rep = n_h / n_kv;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -375,33 +376,35 @@ __global__ void __launch_bounds__(FA_THREADS) attn_decode_mma_kernel(const bf16*
         const int r = c / CPR, cc = c - r * CPR;
         cp_async16(sQ + r * LDS + cc * 8, qg + (size_t)(r < n_rep ? r : 0) * D + cc * 8, r < n_rep);
     }
-    const int n_tiles = min(NT, (kv_len - c0 + FA_BKV - 1) / FA_BKV);
-    for (int t = 0; t < n_tiles; ++t) {
-        const int kv0 = c0 + t * FA_BKV;
+    const int n_tiles = min(DEC_CHUNK_MMA / FA_BKV, (kv_len - c0 + FA_BKV - 1) / FA_BKV);
+    auto load_tile = [&](int t) {
+        const int kv0 = c0 + t * FA_BKV, buf = t & 1;
         for (int c = tid; c < FA_BKV * CPR; c += FA_THREADS) {
             const int r = c / CPR, cc = c - r * CPR;
             const bool ok = (kv0 + r) < kv_len;
             const size_t off = (size_t)(ok ? kv0 + r : 0) * D + cc * 8;
-            cp_async16(sK + (t * FA_BKV + r) * LDS + cc * 8, kg + off, ok);
-            cp_async16(sV + (t * FA_BKV + r) * LDS + cc * 8, vg + off, ok);
+            cp_async16(sK + (buf * FA_BKV + r) * LDS + cc * 8, kg + off, ok);
+            cp_async16(sV + (buf * FA_BKV + r) * LDS + cc * 8, vg + off, ok);
         }
         cp_async_commit();                                  // (the q rows ride in the first group)
-    }
+    };
+    load_tile(0);
+    if (n_tiles > 1) load_tile(1);
     float o[D / 8][4];
 #pragma unroll
     for (int i = 0; i < D / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
     float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
     uint32_t qf[D / 16][4];
     for (int t = 0; t < n_tiles; ++t) {
-        if (t == 0 && n_tiles > 1) cp_async_wait<1>(); else cp_async_wait<0>();
+        if (t + 1 < n_tiles) cp_async_wait<1>(); else cp_async_wait<0>();     // tile t has landed (t+1 may be in flight)
         __syncthreads();
         if (t == 0) {
 #pragma unroll
             for (int ks = 0; ks < D / 16; ++ks)
                 ldmatrix_x4(qf[ks], sQ + (lane & 15) * LDS + ks * 16 + (lane >> 4) * 8);
         }
-        const bf16* sKb = sK + (t * FA_BKV + warp * 16) * LDS;     // this warp's 16 keys of the tile
-        const bf16* sVb = sV + (t * FA_BKV + warp * 16) * LDS;
+        const bf16* sKb = sK + ((t & 1) * FA_BKV + warp * 16) * LDS;     // this warp's 16 keys of the tile
+        const bf16* sVb = sV + ((t & 1) * FA_BKV + warp * 16) * LDS;
         float sc[2][4];
 #pragma unroll
         for (int i = 0; i < 2; ++i) sc[i][0] = sc[i][1] = sc[i][2] = sc[i][3] = 0.f;
@@ -466,6 +469,10 @@ __global__ void __launch_bounds__(FA_THREADS) attn_decode_mma_kernel(const bf16*
             mma_bf16_16816(o[2 * dp], pf, bfr[0], bfr[1]);
             mma_bf16_16816(o[2 * dp + 1], pf, bfr[2], bfr[3]);
         }
+        if (t + 2 < n_tiles) {
+            __syncthreads();                                // every warp is done with this buffer
+            load_tile(t + 2);
+        }
     }
     // ---- merge the 4 warps' states (rows g and g+8 of each thread) through shared memory; only rows < n_rep matter
     __syncthreads();                                        // everyone is done with the K / V tiles
@@ -511,11 +518,11 @@ __global__ void __launch_bounds__(FA_THREADS) attn_decode_mma_kernel(const bf16*
 
 template <int D>
 __global__ void attn_decode_reduce_kernel(const float* __restrict__ ws, bf16* __restrict__ out,
-                                          const int32_t* __restrict__ kv_len_dev, int n_h, int n_kv, int n_splits) {
+                                          const int32_t* __restrict__ kv_len_dev, int n_h, int n_kv, int n_splits, int chunk) {
     const int h = blockIdx.x, b = blockIdx.y, dd = threadIdx.x;
     const int n_rep = n_h / n_kv, kvh = h / n_rep, r = h - kvh * n_rep;
     const int kv_len = *kv_len_dev;
-    const int ns = min(n_splits, (kv_len + DEC_CHUNK - 1) / DEC_CHUNK);
+    const int ns = min(n_splits, (kv_len + chunk - 1) / chunk);
     const float* base = ws + ((size_t)b * n_kv + kvh) * n_splits * dec_rec_floats(n_rep, D);
     float M = -INFINITY;
     for (int s = 0; s < ns; ++s) M = fmaxf(M, base[s * dec_rec_floats(n_rep, D) + r]);
@@ -603,30 +610,32 @@ int tl_attn_decode_fwd(const void* q, const void* k_cache, const void* v_cache, 
     // split phase on tensor cores (attn_decode_mma_kernel) unless TL_DECODE_ATTN=simt asks for the CUDA-core kernel
     const char* impl = getenv("TL_DECODE_ATTN");
     if (!(impl && impl[0] == 's')) {
-        const size_t smem = (size_t)(16 + 2 * DEC_CHUNK) * (d + 8) * sizeof(bf16);
+        const int ns_m = (T_max + DEC_CHUNK_MMA - 1) / DEC_CHUNK_MMA;
+        const dim3 gm(ns_m, n_kv, B);
+        const size_t smem = (size_t)(16 + 4 * FA_BKV) * (d + 8) * sizeof(bf16);
         if (d == 64) {
             static bool done = false;
             if (!done) { cudaFuncSetAttribute(attn_decode_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); done = true; }
-            attn_decode_mma_kernel<64><<<g1, FA_THREADS, smem, st>>>((const bf16*)q, (const bf16*)k_cache, (const bf16*)v_cache,
-                                                                    (float*)workspace, kv_len_dev, n_h, n_kv, T_max, n_splits, sl2);
-            attn_decode_reduce_kernel<64><<<g2, 64, 0, st>>>((const float*)workspace, (bf16*)out, kv_len_dev, n_h, n_kv, n_splits);
+            attn_decode_mma_kernel<64><<<gm, FA_THREADS, smem, st>>>((const bf16*)q, (const bf16*)k_cache, (const bf16*)v_cache,
+                                                                    (float*)workspace, kv_len_dev, n_h, n_kv, T_max, ns_m, sl2);
+            attn_decode_reduce_kernel<64><<<g2, 64, 0, st>>>((const float*)workspace, (bf16*)out, kv_len_dev, n_h, n_kv, ns_m, DEC_CHUNK_MMA);
         } else {
             static bool done = false;
             if (!done) { cudaFuncSetAttribute(attn_decode_mma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); done = true; }
-            attn_decode_mma_kernel<128><<<g1, FA_THREADS, smem, st>>>((const bf16*)q, (const bf16*)k_cache, (const bf16*)v_cache,
-                                                                     (float*)workspace, kv_len_dev, n_h, n_kv, T_max, n_splits, sl2);
-            attn_decode_reduce_kernel<128><<<g2, 128, 0, st>>>((const float*)workspace, (bf16*)out, kv_len_dev, n_h, n_kv, n_splits);
+            attn_decode_mma_kernel<128><<<gm, FA_THREADS, smem, st>>>((const bf16*)q, (const bf16*)k_cache, (const bf16*)v_cache,
+                                                                     (float*)workspace, kv_len_dev, n_h, n_kv, T_max, ns_m, sl2);
+            attn_decode_reduce_kernel<128><<<g2, 128, 0, st>>>((const float*)workspace, (bf16*)out, kv_len_dev, n_h, n_kv, ns_m, DEC_CHUNK_MMA);
         }
         return check_launch("tl_attn_decode_fwd");
     }
     if (d == 64) {
         attn_decode_split_kernel<64><<<g1, DEC_THREADS, 0, st>>>((const bf16*)q, (const bf16*)k_cache, (const bf16*)v_cache,
                                                                   (float*)workspace, kv_len_dev, n_h, n_kv, T_max, n_splits, sl2);
-        attn_decode_reduce_kernel<64><<<g2, 64, 0, st>>>((const float*)workspace, (bf16*)out, kv_len_dev, n_h, n_kv, n_splits);
+        attn_decode_reduce_kernel<64><<<g2, 64, 0, st>>>((const float*)workspace, (bf16*)out, kv_len_dev, n_h, n_kv, n_splits, DEC_CHUNK);
     } else {
         attn_decode_split_kernel<128><<<g1, DEC_THREADS, 0, st>>>((const bf16*)q, (const bf16*)k_cache, (const bf16*)v_cache,
                                                                    (float*)workspace, kv_len_dev, n_h, n_kv, T_max, n_splits, sl2);
-        attn_decode_reduce_kernel<128><<<g2, 128, 0, st>>>((const float*)workspace, (bf16*)out, kv_len_dev, n_h, n_kv, n_splits);
+        attn_decode_reduce_kernel<128><<<g2, 128, 0, st>>>((const float*)workspace, (bf16*)out, kv_len_dev, n_h, n_kv, n_splits, DEC_CHUNK);
     }
     return check_launch("tl_attn_decode_fwd");
 }

@@ -43,10 +43,10 @@ class StageTorchOptimizer:
 
 
 def create_distributed_optimizer(model, optimizer_type=None, **optimizer_kwargs):
-    name = getattr(optimizer_type, "__name__", "Adam") if optimizer_type is not None else "Adam"
+    if optimizer_type is not None and not (isinstance(optimizer_type, type) and issubclass(optimizer_type, torch.optim.Optimizer)):
+        raise TypeError(f"optimizer must be a torch.optim.Optimizer subclass (or None for Adam), got {optimizer_type!r}")
+    name = optimizer_type.__name__ if optimizer_type is not None else "Adam"
     if name in ("Adam", "AdamW"):
         from .train import StageAdam
         return StageAdam(model, decoupled=(name == "AdamW"), **optimizer_kwargs)
-    if not (isinstance(optimizer_type, type) and issubclass(optimizer_type, torch.optim.Optimizer)):
-        raise TypeError(f"optimizer must be a torch.optim.Optimizer subclass, got {optimizer_type!r}")
     return StageTorchOptimizer(model, optimizer_type, **optimizer_kwargs)

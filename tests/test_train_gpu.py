@@ -249,7 +249,11 @@ def test_upstream_gradient_scales_every_parameter():
         (dm(ids, labels=ids).loss * 0.5).backward()
         half = dm.stage.params.hf_state_dict(grads=True)
         for k, v in full.items():
-            assert torch.equal(half[k].float() * 2, v.float()), k   # a power of two: exact in bf16
+            if "norm" in k or k.endswith(".bias"):
+                # gains / biases are summed over row blocks with fp32 atomics: the order varies from run to run
+                assert O.rel_l2(half[k].float() * 2, v.float()) <= 2e-3, k
+            else:
+                assert torch.equal(half[k].float() * 2, v.float()), k   # a power of two: exact in bf16
         # accumulation: a second backward without zero_grad adds the same gradient again
         (dm(ids, labels=ids).loss * 0.5).backward()
         acc = dm.stage.params.hf_state_dict(grads=True)
