@@ -383,9 +383,16 @@ def parity_self_check(N, rank, world):
                               link=StageLink(0, 1))
         ls = ds(tids, labels=tids)
         ls.loss.backward()
-        # this rank's gradients == the same layers' gradients of the single-stage run (same kernels, same shapes)
+        # this rank's gradients == the same layers' gradients of the single-stage run (same kernels, same shapes): weight
+        # matrices bit for bit (one GEMM each); norm gains / biases are summed over row blocks with fp32 atomics, whose
+        # order varies from run to run, so those are compared to 2e-3
         gp, gs = dt.stage.params.hf_state_dict(grads=True), ds.stage.params.hf_state_dict(grads=True)
-        g_eq = all(torch.equal(v, gs[k]) for k, v in gp.items() if ".layers." in k)
+
+        def same(k, a, b):
+            if "norm" in k or k.endswith(".bias"):
+                return float((a.float() - b.float()).norm()) <= 2e-3 * float(b.float().norm()) + 1e-12
+            return torch.equal(a, b)
+        g_eq = all(same(k, v, gs[k]) for k, v in gp.items() if ".layers." in k)
         t = torch.tensor([abs(float(lp.loss) - float(ls.loss)), 0.0 if g_eq else 1.0], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         res["train_loss_pipeline"], res["train_loss_single_stage"] = float(lp.loss), float(ls.loss)
