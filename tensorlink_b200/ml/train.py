@@ -29,6 +29,7 @@ from .module import CausalLMOutput
 
 A_MN, B_MN, ACC = nat.A_MN_MAJOR, nat.B_MN_MAJOR, nat.EPI_ACCUM
 HEAD_CHUNK = 2048          # tokens per fused lm_head + CE pass
+HEAD_STASH_BYTES = 32 << 30  # most d(logits) a pipelined step may keep for the split head backward (7B, 64 x 512: 10 GB)
 
 
 class StageTrainer:
@@ -89,6 +90,8 @@ class StageTrainer:
         self.head_pending: Optional[torch.Tensor] = None
         self.head_norm_pending: Optional[torch.Tensor] = None
         self._head_pending_live = False
+        self.head_split, self._head_w_done, self._head_scale = False, False, 1.0
+        self.head_stash: Dict[str, torch.Tensor] = {}
         self.embed_pending: Optional[torch.Tensor] = None          # tied embedding on another rank than the head
 
     # ------------------------------------------------------------------------------------------ step set-up
@@ -105,14 +108,22 @@ class StageTrainer:
         self.defer_w = n_mb > 1
         self.layer_events, self.final_order = {}, []
         self._head_pending_live = False
+        self.head_split = False
         if not self.defer_w:
             return
         key = (n_mb, self.tok_mb)
+        # the head's own backward leaves the forward phase when its d(logits) fit (HEAD_STASH_BYTES): see head_loss_and_grad
+        self.head_split = bool(self.st.has_head) and n_mb * self.tok_mb * self.cfg.vocab * 2 <= HEAD_STASH_BYTES
         if self._stash_key != key:
             cfg, dev, bf = self.cfg, self.p.device, torch.bfloat16
             n = n_mb * self.tok_mb
             self.stash = {}
+            self.head_stash = {}
             torch.cuda.empty_cache()
+            if self.head_split:
+                self.head_stash = {"hn": torch.empty(n, cfg.hidden, dtype=bf, device=dev),
+                                   "dlogits": torch.empty(n, cfg.vocab, dtype=bf, device=dev),
+                                   "rstd": torch.empty(n, dtype=torch.float32, device=dev)}
             for j in range(len(self.layer_ids)):
                 self.stash[j] = {
                     "h1": torch.empty(n, cfg.hidden, dtype=bf, device=dev), "attn": torch.empty(n, cfg.q_dim, dtype=bf, device=dev),
@@ -184,10 +195,27 @@ class StageTrainer:
         N = b * S
         x2 = x.reshape(N, H)
         labels = shift_labels.reshape(N).contiguous()
-        dx = torch.empty_like(x2)
         if self.head_pending is None:
             self.head_pending = torch.empty(cfg.vocab, H, dtype=torch.bfloat16, device=x.device)
             self.head_norm_pending = torch.zeros(H, dtype=torch.float32, device=x.device)
+        rows = self._rows(mb) if (self.head_split and N == self.tok_mb) else None
+        if rows is not None:
+            # Pipelined step: only logits + loss here.  The fused form below puts 3 lm_head-sized GEMMs (7 decoder layers'
+            # worth of forward work at 7B) into the last stage's FORWARD phase, which every other stage then waits for
+            # before the first gradient can flow back; split, the forward phase carries one of them, the dgrad chain one
+            # (``head_backward``) and the weight gradient joins the deferred ones (``weight_grads``), one GEMM over all
+            # tokens.  d(logits) replace the logits in place and stay in the stash until then.
+            hs = self.head_stash
+            nat.rmsnorm_fwd(x2, v["norm"], cfg.rms_eps, rstd=hs["rstd"][rows], out=hs["hn"][rows])
+            logits = nat.gemm(hs["hn"][rows], v["head"], out=hs["dlogits"][rows])
+            nat.ce_fwd_bwd(logits, labels, self.loss_sum, self.n_valid_dev, logits, inv_n)
+            if not self._head_pending_live:
+                self.head_norm_pending.zero_()
+                self._head_pending_live = True
+            self.ctx[mb]["x_out"] = x2
+            self.launches += 3
+            return
+        dx = torch.empty_like(x2)
         for a in range(0, N, HEAD_CHUNK):
             e = min(N, a + HEAD_CHUNK)
             xc = x2[a:e]
@@ -205,10 +233,31 @@ class StageTrainer:
             self.launches += 6
         self.ctx[mb]["dx_out"] = dx.view(b, S, H)
 
+    def head_backward(self, mb, scale: float) -> torch.Tensor:
+        """Last stage, start of the dgrad chain of micro-batch ``mb``: gradient of the stage's last hidden state — from the
+        fused forward (``dx_out``), or, in a split step, d(logits)·W_head and the final norm's backward now."""
+        c = self.ctx[mb]
+        if "dx_out" in c:
+            dy = c.pop("dx_out")
+            return dy * scale if scale != 1.0 else dy
+        cfg, v, hs, rows = self.cfg, self.p.v, self.head_stash, self._rows(mb)
+        x2 = c.pop("x_out")
+        dhn = nat.gemm(hs["dlogits"][rows], v["head"], flags=B_MN, N=cfg.hidden)          # [n,V]·[V,H]
+        dx = torch.empty_like(x2)
+        nat.rmsnorm_bwd(x2, v["norm"], dhn, hs["rstd"][rows], dx, self.head_norm_pending)
+        self.launches += 2
+        if scale != 1.0:
+            dx = dx * scale
+        return dx.view(c["b"], c["S"], cfg.hidden)
+
     def commit_head(self, scale: float) -> Optional[torch.Tensor]:
         """backward() on the last stage: pending lm_head / final-norm gradients x upstream gradient -> arena.
-        Returns the scaled lm_head gradient of THIS backward (the tied-embedding exchange needs the delta alone)."""
+        Returns the scaled lm_head gradient of THIS backward (the tied-embedding exchange needs the delta alone).
+        In a split step this runs after the dgrad chains (from ``weight_grads``), once the pending buffers are complete."""
         if not self._head_pending_live:
+            return None
+        if self.head_split and not self._head_w_done:
+            self._head_scale = scale             # nothing to commit yet: weight_grads() produces the gradient, then commits
             return None
         self._head_pending_live = False
         if self.cfg.tied and not self.st.has_embed:
@@ -290,6 +339,13 @@ class StageTrainer:
             return
         cfg, g = self.cfg, self.p.g
         H, n = cfg.hidden, self.n_mb * self.tok_mb
+        if self.head_split and self._head_pending_live:
+            hs = self.head_stash
+            nat.gemm(hs["dlogits"], hs["hn"], out=self.head_pending, flags=A_MN | B_MN, M=cfg.vocab, K=n, N=H)   # dW = dlogits^T·hn
+            self.launches += 1
+            self._head_w_done = True
+            self.commit_head(self._head_scale)
+            self._head_w_done = False
         for j in reversed(range(len(self.layer_ids))):
             li, st = self.layer_ids[j], self.stash[j]
             nat.gemm(st["dy"], st["act"], out=g[f"l{li}.wd"], flags=A_MN | B_MN | self._acc(f"l{li}.wd"), M=H, K=n, N=cfg.intermediate)
@@ -443,7 +499,9 @@ def train_backward(dm, grad_scale: float = 1.0):
         tr.embed_pending.zero_()
         embed_into = tr.embed_pending
     for m in reversed(range(s["n_mb"])):
-        if link.last:
+        if link.last and hasattr(tr, "head_backward"):
+            dy = tr.head_backward(m, grad_scale)
+        elif link.last:
             dy = tr.ctx[m].pop("dx_out")
             if grad_scale != 1.0:
                 dy = dy * grad_scale
@@ -461,6 +519,8 @@ def train_backward(dm, grad_scale: float = 1.0):
     link.flush()
     if hasattr(tr, "weight_grads"):
         tr.weight_grads()
+        if link.last and head_delta is None and getattr(tr, "head_split", False):
+            head_delta = tr.head_pending         # split step: the lm_head gradient of this backward exists only now
     tr.finish_backward()
     if tied_split:
         # module.py:1218-1265 ties lm_head to embed_tokens on the host; here the two copies live on different ranks.
@@ -538,7 +598,7 @@ class StageAdam:
         p = self.dm.stage.params
         tr = _trainer(self.dm)
         import os
-        if not getattr(tr, "overlap_ok", False) or not p.flat.is_cuda or os.environ.get("TL_ADAM_OVERLAP", "1") == "0":
+        if not getattr(tr, "overlap_ok", False) or not p.flat.is_cuda or os.environ.get("TL_ADAM_OVERLAP", "0") != "1":
             self._update(0, p.numel)
             return
         tr.overlap_ok = False
