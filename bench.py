@@ -431,7 +431,7 @@ def measure_training(args, N, rank, world, tf_peak, peak_kind):
     from tensorlink_b200.ml.weights import synthetic_tokens
     cfg = get_config(args.train_model)
     B, S = args.train_batch * N, args.train_seq
-    n_mb = N if N == 1 else args.train_mb_per_stage * N    # more micro-batches than stages: bubble (N-1)/(n_mb+N-1)
+    n_mb = N if N == 1 else min(args.train_mb_per_stage * N, B)    # more micro-batches than stages: bubble (N-1)/(n_mb+N-1)
     dm = DistributedModel(args.train_model, training=True, n_pipelines=n_mb, max_batch=B, max_seq=S, init="device",
                           optimizer=torch.optim.Adam, max_tokens=8, balanced_plan=N > 1)
     opt = dm.create_optimizer(lr=1e-4)
@@ -486,8 +486,9 @@ def measure_training(args, N, rank, world, tf_peak, peak_kind):
     tf_burst = burst_tflops(tf_peak)
     res = {"metric": "training samples/sec", "value": B * args.steps / t, "unit": "samples/s", "ms_per_step": t / args.steps * 1e3,
            "loss": float(loss.detach()), "config": {"workload": f"{args.train_model} bf16, one optimizer step (fwd + bwd + Adam), "
-                                                       f"global batch {B} x seq {S}, {n_mb} micro-batch(es), {N} stage(s); schedule: all forwards, then the dgrad chain of every micro-batch, "
-                                                       "then each stage's weight gradients as one GEMM per weight over all micro-batches, Adam layer by layer on a side stream",
+                                                       f"global batch {B} x seq {S}, {n_mb} micro-batch(es), {N} stage(s); schedule: all forwards (last stage: logits + loss only), then the dgrad chain of every micro-batch "
+                                                       "(starting with the lm_head dgrad), then each stage's weight gradients as one GEMM per weight over all micro-batches, "
+                                                       "then one fused Adam launch over the stage's arena",
                                            "h2d_bytes_per_step": B * S * 8, "d2h_bytes_per_step": 4},
            "model_tflops_per_s": flops * args.steps / t / 1e12, "gpu_launches": tr.launches - l0,
            "roofline": {"bound": "tensor", "kernel": "tcgen05 GEMM (gate/up forward Linear of one layer, timed alone)", "achieved": ach,
@@ -525,7 +526,7 @@ def main():
     ap.add_argument("--train-model", default="Qwen/Qwen2.5-7B")
     ap.add_argument("--train-batch", type=int, default=8)
     ap.add_argument("--train-seq", type=int, default=512)
-    ap.add_argument("--train-mb-per-stage", type=int, default=2, help="micro-batches per pipeline stage in the training step (N > 1)")
+    ap.add_argument("--train-mb-per-stage", type=int, default=4, help="micro-batches per pipeline stage in the training step (N > 1)")
     args = ap.parse_args()
     name, prompt, new, wl_rows = WORKLOADS[args.workload]
     prompt, new = args.prompt or prompt, args.new or new

@@ -20,7 +20,7 @@ def main():
     ap.add_argument("--train-model", default="Qwen/Qwen2.5-7B")
     ap.add_argument("--train-batch", type=int, default=8)
     ap.add_argument("--train-seq", type=int, default=512)
-    ap.add_argument("--train-mb-per-stage", type=int, default=2)
+    ap.add_argument("--train-mb-per-stage", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true", default=True)
     args = ap.parse_args()
     import torch
