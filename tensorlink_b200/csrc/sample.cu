@@ -122,13 +122,11 @@ __global__ void __launch_bounds__(SM_THREADS) sample_kernel(const bf16* __restri
         k_key = s_sel[1];
     }
     // ---- probability mass per thread over the bins that survive top-k (fixed order -> deterministic)
-    double mass[1];
     double local_m = 0.0;
     for (int j = 0; j < SM_PER; ++j) {
         const int key = hi_key - j;
         if (cnt[j] && key >= k_key) local_m += (double)cnt[j] * (double)__expf(key_value((uint32_t)key) * inv_temp - x_max);
     }
-    (void)mass;
     double Z;
     const double m_before = block_excl_scan(local_m, s_warp, &Z);
     // ---- top-p: keep a bin while the mass above it is < top_p * Z; the lowest kept bin is the threshold

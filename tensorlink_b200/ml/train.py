@@ -11,7 +11,9 @@ Here each rank owns its stage's flat parameter and gradient arenas; the backward
 tcgen05 GEMMs (dgrad + wgrad, MN-major operands, gradient accumulation in the epilogue) plus the attention /
 norm / RoPE / SwiGLU backward kernels; gradients of ``hidden_states`` hop rank i+1 -> i over NVLink.  The loss and
 its gradient are produced on the last stage by a fused lm_head + cross-entropy pass over token chunks, so the
-[tokens, vocab] logits never exist in full.  The object returned as ``.loss`` is an autograd proxy on EVERY rank:
+[tokens, vocab] logits never exist in full (one micro-batch); in a pipelined step only logits + loss run in the forward
+phase and the head's dgrad / wgrad join the backward chain / the deferred weight gradients (``head_loss_and_grad``).
+The object returned as ``.loss`` is an autograd proxy on EVERY rank:
 ``loss.backward()`` runs that rank's part of the pipeline backward (SPMD equivalent of the autograd router).
 
 Tied embeddings split over two ranks (Qwen2.5-0.5B at N > 1): the two copies' gradients are summed rank 0 <-> last
@@ -19,6 +21,7 @@ rank before the optimizer step, so both copies take identical updates.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -597,7 +600,6 @@ class StageAdam:
         self.t += 1
         p = self.dm.stage.params
         tr = _trainer(self.dm)
-        import os
         if not getattr(tr, "overlap_ok", False) or not p.flat.is_cuda or os.environ.get("TL_ADAM_OVERLAP", "0") != "1":
             self._update(0, p.numel)
             return
