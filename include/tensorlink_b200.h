@@ -109,9 +109,7 @@ int tl_attn_prefill_fwd(const void* q, const void* k_cache, const void* v_cache,
                         int S, int past_len, int n_h, int n_kv, int d, int T_max, float scale, void* stream);
 
 /* ---- K4  decode attention, one query token per batch row, split over the KV length.
- * kv_len_dev: device int32, number of valid keys (same for all rows).  workspace >= tl_attn_decode_ws(...), ZEROED
- * once by the caller before its first use: its tail holds arrival counters that every launch returns to zero (the
- * split CTA that publishes the last partial of a (row, kv head) merges them; there is no second launch). */
+ * kv_len_dev: device int32, number of valid keys (same for all rows).  workspace >= tl_attn_decode_ws(...) */
 size_t tl_attn_decode_ws(int B, int n_h, int d, int T_max);
 int tl_attn_decode_fwd(const void* q, const void* k_cache, const void* v_cache, void* out,
                        const int32_t* kv_len_dev, void* workspace, size_t ws_bytes, int B, int n_h, int n_kv,

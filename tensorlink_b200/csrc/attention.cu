@@ -354,8 +354,7 @@ template <int D>
 __global__ void __launch_bounds__(FA_THREADS) attn_decode_mma_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k_cache,
                                                                       const bf16* __restrict__ v_cache, float* __restrict__ ws,
                                                                       const int32_t* __restrict__ kv_len_dev, int n_h, int n_kv,
-                                                                      int T_max, int n_splits, float scale_log2,
-                                                                      bf16* __restrict__ out, int* __restrict__ arrivals) {
+                                                                      int T_max, int n_splits, float scale_log2) {
     constexpr int LDS = D + 8;
     constexpr int CPR = D / 8;
     constexpr int NT = 2;                                  // shared-memory ring: two 64-key tiles
@@ -515,38 +514,6 @@ __global__ void __launch_bounds__(FA_THREADS) attn_decode_mma_kernel(const bf16*
         rec[r] = m;
         rec[n_rep + r] = l;
     }
-    if (arrivals == nullptr) return;                        // two-kernel form: attn_decode_reduce_kernel follows
-    // ---- fused reduce: the CTA that publishes the LAST record of this (row, kv head) merges all of them.  Saves the
-    // reduce launch and its dependent-load latency (10.8 us per layer at 5 splits under ncu); the arrival counter returns
-    // to zero for the next launch.
-    __shared__ int s_last;
-    __threadfence();                                        // this CTA's record is visible device-wide before it is counted
-    __syncthreads();
-    const int n_active = (kv_len + DEC_CHUNK_MMA - 1) / DEC_CHUNK_MMA;
-    if (tid == 0) {
-        const int old = atomicAdd(&arrivals[b * n_kv + kvh], 1);
-        s_last = (old == n_active - 1);
-        if (s_last) arrivals[b * n_kv + kvh] = 0;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    const float* base = ws + ((size_t)b * n_kv + kvh) * n_splits * dec_rec_floats(n_rep, D);
-    const int stride = dec_rec_floats(n_rep, D);
-    for (int i = tid; i < n_rep * D; i += FA_THREADS) {
-        const int r = i / D;
-        float M = -INFINITY;
-        for (int s2 = 0; s2 < n_active; ++s2) M = fmaxf(M, __ldcg(base + s2 * stride + r));
-        float L = 0.f, O = 0.f;
-#pragma unroll 4
-        for (int s2 = 0; s2 < n_active; ++s2) {
-            const float* rc = base + s2 * stride;
-            const float w = exp2f(__ldcg(rc + r) - M);
-            L += __ldcg(rc + n_rep + r) * w;
-            O += __ldcg(rc + 2 * n_rep + i) * w;
-        }
-        out[((size_t)b * n_h + kvh * n_rep) * D + i] = f2bf(L > 0.f ? O / L : 0.f);
-    }
 }
 
 template <int D>
@@ -622,8 +589,7 @@ int tl_attn_prefill_fwd(const void* q, const void* k_cache, const void* v_cache,
 
 size_t tl_attn_decode_ws(int B, int n_h, int d, int T_max) {
     const size_t n_splits = (size_t)(T_max + tl::DEC_CHUNK - 1) / tl::DEC_CHUNK;
-    // records of the split phase, then one arrival counter per (row, kv head; at most one per head) for the fused reduce
-    return (size_t)B * n_splits * (size_t)n_h * (2 + d) * sizeof(float) + (size_t)B * (size_t)n_h * sizeof(int);
+    return (size_t)B * n_splits * (size_t)n_h * (2 + d) * sizeof(float);
 }
 
 int tl_attn_decode_fwd(const void* q, const void* k_cache, const void* v_cache, void* out, const int32_t* kv_len_dev,
@@ -641,28 +607,24 @@ int tl_attn_decode_fwd(const void* q, const void* k_cache, const void* v_cache, 
     const float sl2 = scale * 1.4426950408889634f;
     cudaStream_t st = (cudaStream_t)stream;
     const dim3 g1(n_splits, n_kv, B), g2(n_h, B);
-    // split phase on tensor cores (attn_decode_mma_kernel) unless TL_DECODE_ATTN=simt asks for the CUDA-core kernel;
-    // TL_DECODE_ATTN=mma2 keeps the reduce as a second launch (default: fused into the split kernel, last arriver merges)
+    // split phase on tensor cores (attn_decode_mma_kernel) unless TL_DECODE_ATTN=simt asks for the CUDA-core kernel
     const char* impl = getenv("TL_DECODE_ATTN");
     if (!(impl && impl[0] == 's')) {
         const int ns_m = (T_max + DEC_CHUNK_MMA - 1) / DEC_CHUNK_MMA;
         const dim3 gm(ns_m, n_kv, B);
         const size_t smem = (size_t)(16 + 4 * FA_BKV) * (d + 8) * sizeof(bf16);
-        const bool two = impl && impl[0] == 'm' && impl[1] == 'm' && impl[2] == 'a' && impl[3] == '2';
-        int* arrivals = two ? nullptr
-                            : reinterpret_cast<int*>((unsigned char*)workspace + (size_t)B * n_splits * (size_t)n_h * (2 + d) * sizeof(float));
         if (d == 64) {
             static bool done = false;
             if (!done) { cudaFuncSetAttribute(attn_decode_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); done = true; }
             attn_decode_mma_kernel<64><<<gm, FA_THREADS, smem, st>>>((const bf16*)q, (const bf16*)k_cache, (const bf16*)v_cache,
-                                                                    (float*)workspace, kv_len_dev, n_h, n_kv, T_max, ns_m, sl2, (bf16*)out, arrivals);
-            if (two) attn_decode_reduce_kernel<64><<<g2, 64, 0, st>>>((const float*)workspace, (bf16*)out, kv_len_dev, n_h, n_kv, ns_m, DEC_CHUNK_MMA);
+                                                                    (float*)workspace, kv_len_dev, n_h, n_kv, T_max, ns_m, sl2);
+            attn_decode_reduce_kernel<64><<<g2, 64, 0, st>>>((const float*)workspace, (bf16*)out, kv_len_dev, n_h, n_kv, ns_m, DEC_CHUNK_MMA);
         } else {
             static bool done = false;
             if (!done) { cudaFuncSetAttribute(attn_decode_mma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); done = true; }
             attn_decode_mma_kernel<128><<<gm, FA_THREADS, smem, st>>>((const bf16*)q, (const bf16*)k_cache, (const bf16*)v_cache,
-                                                                     (float*)workspace, kv_len_dev, n_h, n_kv, T_max, ns_m, sl2, (bf16*)out, arrivals);
-            if (two) attn_decode_reduce_kernel<128><<<g2, 128, 0, st>>>((const float*)workspace, (bf16*)out, kv_len_dev, n_h, n_kv, ns_m, DEC_CHUNK_MMA);
+                                                                     (float*)workspace, kv_len_dev, n_h, n_kv, T_max, ns_m, sl2);
+            attn_decode_reduce_kernel<128><<<g2, 128, 0, st>>>((const float*)workspace, (bf16*)out, kv_len_dev, n_h, n_kv, ns_m, DEC_CHUNK_MMA);
         }
         return check_launch("tl_attn_decode_fwd");
     }

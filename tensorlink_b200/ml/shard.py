@@ -224,7 +224,7 @@ class CudaLayerGroup:
         # too few output tiles to occupy every SM
         self.gemm_ws = (torch.empty(nat.gemm_splitk_ws(min(max_batch, 128), max(cfg.qkv_dim, cfg.hidden)), dtype=torch.uint8,
                                     device=dev) if max_batch > 1 else None)
-        self.dec_ws = torch.zeros(max(nat.attn_decode_ws(max_batch, cfg.n_heads, cfg.head_dim, max_seq), 16),     # (arrival counters start at 0)
+        self.dec_ws = torch.empty(max(nat.attn_decode_ws(max_batch, cfg.n_heads, cfg.head_dim, max_seq), 16),
                                   dtype=torch.uint8, device=dev)
         self.scale = cfg.head_dim ** -0.5
         self.allow_chain = True              # DistributedModel clears it when NCCL kernels share the device during decode

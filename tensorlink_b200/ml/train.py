@@ -115,25 +115,29 @@ class StageTrainer:
         if not self.defer_w:
             return
         key = (n_mb, self.tok_mb)
-        # the head's own backward leaves the forward phase when its d(logits) fit (HEAD_STASH_BYTES): see head_loss_and_grad
-        self.head_split = bool(self.st.has_head) and n_mb * self.tok_mb * self.cfg.vocab * 2 <= HEAD_STASH_BYTES
-        if self._stash_key != key:
-            cfg, dev, bf = self.cfg, self.p.device, torch.bfloat16
-            n = n_mb * self.tok_mb
-            self.stash = {}
-            self.head_stash = {}
-            torch.cuda.empty_cache()
-            if self.head_split:
-                self.head_stash = {"hn": torch.empty(n, cfg.hidden, dtype=bf, device=dev),
-                                   "dlogits": torch.empty(n, cfg.vocab, dtype=bf, device=dev),
-                                   "rstd": torch.empty(n, dtype=torch.float32, device=dev)}
-            for j in range(len(self.layer_ids)):
-                self.stash[j] = {
-                    "h1": torch.empty(n, cfg.hidden, dtype=bf, device=dev), "attn": torch.empty(n, cfg.q_dim, dtype=bf, device=dev),
-                    "h2": torch.empty(n, cfg.hidden, dtype=bf, device=dev), "act": torch.empty(n, cfg.intermediate, dtype=bf, device=dev),
-                    "dy": torch.empty(n, cfg.hidden, dtype=bf, device=dev), "dgu": torch.empty(n, 2 * cfg.intermediate, dtype=bf, device=dev),
-                    "d_xmid": torch.empty(n, cfg.hidden, dtype=bf, device=dev), "dqkv": torch.empty(n, cfg.qkv_dim, dtype=bf, device=dev)}
-            self._stash_key = key
+        if self._stash_key == key:
+            self.head_split = bool(self.head_stash)
+            return
+        cfg, dev, bf = self.cfg, self.p.device, torch.bfloat16
+        n = n_mb * self.tok_mb
+        self.stash, self.head_stash = {}, {}
+        torch.cuda.empty_cache()
+        # the head's own backward leaves the forward phase when its d(logits) fit (see head_loss_and_grad); else the
+        # fused, chunked form runs in the forward phase as in a single-micro-batch step
+        need = n * cfg.vocab * 2
+        self.head_split = (bool(self.st.has_head) and need <= HEAD_STASH_BYTES
+                           and need <= torch.cuda.mem_get_info(dev)[0] // 2)
+        if self.head_split:
+            self.head_stash = {"hn": torch.empty(n, cfg.hidden, dtype=bf, device=dev),
+                               "dlogits": torch.empty(n, cfg.vocab, dtype=bf, device=dev),
+                               "rstd": torch.empty(n, dtype=torch.float32, device=dev)}
+        for j in range(len(self.layer_ids)):
+            self.stash[j] = {
+                "h1": torch.empty(n, cfg.hidden, dtype=bf, device=dev), "attn": torch.empty(n, cfg.q_dim, dtype=bf, device=dev),
+                "h2": torch.empty(n, cfg.hidden, dtype=bf, device=dev), "act": torch.empty(n, cfg.intermediate, dtype=bf, device=dev),
+                "dy": torch.empty(n, cfg.hidden, dtype=bf, device=dev), "dgu": torch.empty(n, 2 * cfg.intermediate, dtype=bf, device=dev),
+                "d_xmid": torch.empty(n, cfg.hidden, dtype=bf, device=dev), "dqkv": torch.empty(n, cfg.qkv_dim, dtype=bf, device=dev)}
+        self._stash_key = key
 
     def _rows(self, mb) -> Optional[slice]:
         """Rows of the stash that belong to micro-batch ``mb`` (None: this call is not part of a deferred step)."""

@@ -297,12 +297,10 @@ def test_attn_prefill(nat, monkeypatch, impl, B, S, past, n_h, n_kv, d):
 @pytest.mark.parametrize("B,kv_len,n_h,n_kv,d", [(1, 1, 14, 2, 64), (2, 127, 4, 2, 128), (1, 128, 28, 4, 128),
                                                  (3, 129, 8, 8, 64), (1, 1000, 28, 4, 128), (2, 2048, 32, 8, 128),
                                                  (32, 4096, 28, 4, 128), (4, 65, 16, 2, 128), (5, 193, 28, 4, 128)])
-@pytest.mark.parametrize("impl", ["mma", "mma2", "simt"])
+@pytest.mark.parametrize("impl", ["mma", "simt"])
 def test_attn_decode(nat, B, kv_len, n_h, n_kv, d, impl, monkeypatch):
-    """split-KV decode attention: the tensor-core split kernel (default: the GQA group's query heads are the MMA's M rows,
-    the last-arriving split CTA merges the partials), the same with a separate reduce launch (TL_DECODE_ATTN=mma2) and the
-    CUDA-core one (TL_DECODE_ATTN=simt) against the oracle; a second launch on the same workspace checks that the arrival
-    counters came back to zero."""
+    """split-KV decode attention: the tensor-core split kernel (default: the GQA group's query heads are the MMA's M rows)
+    and the CUDA-core one (TL_DECODE_ATTN=simt) against the oracle."""
     monkeypatch.setenv("TL_DECODE_ATTN", impl)
     q, k, v, ref, f32 = _attn_case(B, 1, kv_len - 1, n_h, n_kv, d, seed=40)
     T_max = kv_len + 100
@@ -311,16 +309,12 @@ def test_attn_decode(nat, B, kv_len, n_h, n_kv, d, impl, monkeypatch):
     kc[:, :, :kv_len], vc[:, :, :kv_len] = k, v
     kc[:, :, kv_len:] = 50.0        # poison: keys beyond kv_len must be ignored
     out = torch.empty(B, n_h * d, dtype=torch.bfloat16, device="cuda")
-    ws = torch.zeros(nat.attn_decode_ws(B, n_h, d, T_max), dtype=torch.uint8, device="cuda")
+    ws = torch.empty(nat.attn_decode_ws(B, n_h, d, T_max), dtype=torch.uint8, device="cuda")
     kvl = torch.tensor([kv_len], dtype=torch.int32, device="cuda")
-    qd, kd, vd = dev(q.reshape(B, n_h * d)), dev(kc), dev(vc)
-    nat.attn_decode_fwd(qd, kd, vd, out, kvl, ws, B, n_h, n_kv, d, d ** -0.5)
+    nat.attn_decode_fwd(dev(q.reshape(B, n_h * d)), dev(kc), dev(vc), out, kvl, ws, B, n_h, n_kv, d, d ** -0.5)
     got = out.cpu().view(B, 1, -1)
     assert O.rel_l2(got, f32) <= 1.25 * O.rel_l2(ref, f32) + 1e-4
     assert O.rel_l2(got, ref) <= TOL_ATTN
-    out2 = torch.full_like(out, 7.0)
-    nat.attn_decode_fwd(qd, kd, vd, out2, kvl, ws, B, n_h, n_kv, d, d ** -0.5)
-    assert torch.equal(out2, out)
 
 
 @pytest.mark.parametrize("cfg", [C.TINY_QWEN2, C.TINY_QWEN2_D128, C.TINY_QWEN3], ids=lambda c: c.name)
@@ -342,7 +336,7 @@ def test_attn_decode_fused_equals_unfused(nat, cfg, B, past):
     q = torch.empty(B, cfg.q_dim, dtype=torch.bfloat16, device="cuda")
     ref = torch.empty(B, cfg.q_dim, dtype=torch.bfloat16, device="cuda")
     nat.rope_kv_fwd(qkv, q, kc1, vc1, pos, ct, st, qn, kn, cfg.rms_eps, 1, n_h, n_kv, d)
-    ws = torch.zeros(nat.attn_decode_ws(B, n_h, d, T_max), dtype=torch.uint8, device="cuda")
+    ws = torch.empty(nat.attn_decode_ws(B, n_h, d, T_max), dtype=torch.uint8, device="cuda")
     nat.attn_decode_fwd(q, kc1, vc1, ref, kvl, ws, B, n_h, n_kv, d, d ** -0.5)
     kc2, vc2 = kc0.clone(), vc0.clone()
     got = torch.empty_like(ref)
