@@ -261,13 +261,16 @@ template <int M>
 static int launch_stream(const void* x, const void* W, void* y, int N, int K, const void* bias, const void* residual,
                          const void* norm_w, float eps, int flags, const void* pf_ptr, size_t pf_bytes, cudaStream_t st) {
     auto kern = gemv_stream_kernel<M>;
-    // TL_GEMV_CTAS_PER_SM=2: two half-size rings per SM (16 consumer warps, finer work split, and the next kernel's
-    // CTAs can become resident as soon as one of the two exits); 1 = one deep ring per SM
-    static int per_sm = 0;
-    if (per_sm == 0) {
+    // Two half-size rings per SM (16 consumer warps, finer work split, the next kernel's CTAs become resident as soon as
+    // one of the two exits) when an SM's share of W is small — the latency-bound regime of small models: Qwen2.5-0.5B
+    // decode 1210 -> 1343 tok/s (round 2); one deep ring per SM otherwise (7B: 355.1 vs 354.9 tok/s).
+    // TL_GEMV_CTAS_PER_SM=1|2 forces either.
+    static int forced = -1;
+    if (forced < 0) {
         const char* e = getenv("TL_GEMV_CTAS_PER_SM");
-        per_sm = (e && e[0] == '2') ? 2 : 1;
+        forced = (e && e[0] == '2') ? 2 : ((e && e[0] == '1') ? 1 : 0);
     }
+    const int per_sm = forced ? forced : (((size_t)N * K * 2 / (size_t)sm_count() <= (size_t)128 * 1024) ? 2 : 1);
     // TL_GEMV_RING_KB (default 220): shared memory per CTA.  <= 110 leaves room for the NEXT kernel's CTA on the same
     // SM, so under programmatic dependent launch its producer fills its ring while this kernel is still streaming.
     static int ring_kb = 0;
