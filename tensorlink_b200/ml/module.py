@@ -486,25 +486,40 @@ class DistributedModel(torch.nn.Module):
             span[0].record()
         eos_ids = _eos_list(self._eos[0])
         n_cols = max_new
+
+        def collect(m, step):
+            """first stage: ids of micro-batch m for column ``step`` (sent by the last stage in the previous round)"""
+            if multi:
+                link.wait(sent_x[m])                       # x_dec[m] still feeding the previous hop?
+                link.recv_up(st.ids_dec[m][:b], self.world - 1)
+            out_tokens[m * b:(m + 1) * b, step] = st.ids_dec[m][:b]
+
         for step in range(max_new):
+            collected = False
             if eos_ids and step and step % EOS_CHECK_EVERY == 0:
-                # columns 0..step-1 are complete on the first stage: stop once every row has emitted EOS (HF semantics)
+                # Stop once every row has emitted EOS (HF semantics).  The first stage takes this column's ids of EVERY
+                # micro-batch first, so that no send is left without its posted receive when the ranks meet in the
+                # broadcast below (a collective queued behind an unmatched point-to-point op could wait forever).
+                if link.first:
+                    for m in range(n_mb):
+                        collect(m, step)
+                collected = True
                 flag = torch.zeros(1, dtype=torch.int32, device=dev)
-                if link.first and _all_rows_finished(out_tokens[:, :step], eos_ids):
+                if link.first and _all_rows_finished(out_tokens[:, :step + 1], eos_ids):
                     flag.fill_(1)
                 if multi:
                     link.flush()
                     torch.cuda.synchronize(dev)
                     link.broadcast(flag, 0)
                 if int(flag.item()):
-                    n_cols = step
+                    n_cols = step + 1
+                    if streamer is not None and link.first:
+                        streamer.put(out_tokens[:, step].cpu())
                     break
             for m in range(n_mb):
                 if link.first:
-                    if multi:
-                        link.wait(sent_x[m])                       # x_dec[m] still feeding the previous hop?
-                        link.recv_up(st.ids_dec[m][:b], self.world - 1)
-                    out_tokens[m * b:(m + 1) * b, step] = st.ids_dec[m][:b]
+                    if not collected:
+                        collect(m, step)
                     if streamer is not None and m == n_mb - 1:
                         streamer.put(out_tokens[:, step].cpu())         # all rows of this step, one column
                 if step == max_new - 1:

@@ -39,6 +39,21 @@ def main(out_dir):
     os.environ.pop("TL_P2P")
     res["gen_peer_vs_nccl"] = bool(torch.equal(gen, gen_nccl))
 
+    # EOS early stop on both transports: 40 tokens requested, the token the model emits at step 2 of row 0 declared EOS for a
+    # one-row-per-micro-batch run -> every rank returns the same, shortened result as the single stage does
+    ids2 = ids[[0, 0]].contiguous()         # two copies of row 0: both finish at step 2, the loop stops at its next check
+    eos = int(gen[0, 20 + 2])
+    for tag, env in (("peer", None), ("nccl", "nccl")):
+        if env:
+            os.environ["TL_P2P"] = env
+        got = dm.generate(ids2 if rank == 0 else None, max_new_tokens=40, eos_token_id=eos, pad_token_id=0)
+        if env:
+            os.environ.pop("TL_P2P")
+        res[f"eos_{tag}_shape"] = tuple(got.shape)
+        if rank == 0:
+            want = single.generate(ids2, max_new_tokens=40, eos_token_id=eos, pad_token_id=0)
+            res[f"eos_{tag}_equal"] = bool(got.shape == want.shape and torch.equal(got, want) and got.shape[1] < 60)
+
     class Cols:
         def __init__(self):
             self.cols, self.ended = [], False

@@ -29,6 +29,8 @@ def test_two_gpu_pipeline_equals_single_stage(tmp_path):
     assert r0["gen_graph_vs_eager"] and r1["gen_graph_vs_eager"]
     assert r0["used_ring"] and r1["used_ring"] and r0["gen_peer_vs_nccl"] and r1["gen_peer_vs_nccl"] and r0["stream_ok"]
     assert r0["bytes_sent_infer"] > 0 and r1["bytes_sent_infer"] > 0
+    assert r0["eos_peer_equal"] and r0["eos_nccl_equal"]
+    assert r0["eos_peer_shape"] == r1["eos_peer_shape"] and r0["eos_nccl_shape"] == r1["eos_nccl_shape"]
     assert abs(r0["loss"] - r0["loss_single"]) < 1e-5 and abs(r1["loss"] - r0["loss_single"]) < 1e-5
     ref = torch.load(tmp_path / "ref_grads.pt")
     for rank in (0, 1):
