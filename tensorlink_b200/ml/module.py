@@ -363,7 +363,7 @@ class DistributedModel(torch.nn.Module):
         self.timers["generate_wall_s"] = time.perf_counter() - t0
         return apply_eos(result, S, *self._eos)
 
-    def _generate_left_padded(self, input_ids, groups, max_new, streamer, use_graph, sampling):
+    def _generate_left_padded(self, input_ids, groups, shape, max_new, streamer, use_graph, sampling):
         """HF semantics for a left-padded batch: every row attends to its own tokens only, at positions 0..L-1.  Rows of
         equal real length are generated together (one uniform run per length: the KV cache and RoPE positions of a run
         start at the row's first real token, so no pad key exists to be masked); the result keeps HF's layout
@@ -373,7 +373,7 @@ class DistributedModel(torch.nn.Module):
         eos, pad = self._eos
         pad_id = pad if pad is not None else (_eos_list(eos)[0] if eos is not None else 0)
         first = self.link.first
-        B, S = (input_ids.shape if first else (sum(len(r) for r in groups.values()), max(groups)))
+        B, S = shape
         out = torch.full((B, S + max_new), int(pad_id), dtype=torch.int64, device=self.device)
         if first:
             out[:, :S] = input_ids.to(self.device)
@@ -390,7 +390,10 @@ class DistributedModel(torch.nn.Module):
             out[torch.as_tensor(rows, device=self.device), S:S + n_new] = got[:, L:].to(self.device)
             longest = max(longest, n_new)
         self._eos = (eos, pad)
-        return out[:, :S + longest]
+        out = out[:, :S + longest].contiguous()
+        if self.world > 1:
+            self.link.broadcast(out, 0)              # every rank returns the whole result, prompt and pads included
+        return out
 
     # ------------------------------------------------------------------------------------------ generate
     @torch.no_grad()
@@ -423,11 +426,12 @@ class DistributedModel(torch.nn.Module):
         if link.first and mask is not None:
             if tuple(mask.shape) != tuple(input_ids.shape):
                 raise ValueError(f"attention_mask shape {tuple(mask.shape)} != input_ids shape {tuple(input_ids.shape)}")
-            groups = _left_pad_groups(mask)
+            g = _left_pad_groups(mask)
+            groups = None if g is None else (g, tuple(input_ids.shape))
         if self.world > 1:
             groups = link.broadcast_object(groups)
         if groups is not None:
-            return self._generate_left_padded(input_ids, groups, max_new, streamer, use_graph, sampling)
+            return self._generate_left_padded(input_ids, groups[0], groups[1], max_new, streamer, use_graph, sampling)
         shape, sampling = link.broadcast_object((tuple(input_ids.shape), sampling) if link.first else None)
         B, S = shape
         if hasattr(st, "set_sampling"):
@@ -509,7 +513,8 @@ class DistributedModel(torch.nn.Module):
                     flag.fill_(1)
                 if multi:
                     link.flush()
-                    torch.cuda.synchronize(dev)
+                    if torch.device(dev).type == "cuda":
+                        torch.cuda.synchronize(dev)
                     link.broadcast(flag, 0)
                 if int(flag.item()):
                     n_cols = step + 1

@@ -55,6 +55,31 @@ def main(out_dir):
     eos = int(ref_gen2[1, 9 + 2])
     gen_eos = dm2.generate(ids4 if rank == 0 else None, max_new_tokens=5, eos_token_id=eos, pad_token_id=0)
     res["eos_ok"] = bool(torch.equal(gen_eos, apply_eos(ref_gen2, 9, eos, 0)) and gen_eos.shape[1] <= ref_gen2.shape[1])
+    # ... and the loop really stops: 40 tokens requested, both rows (copies of one prompt) emit EOS at step 2, the ranks agree
+    # at the step-16 check (ids in flight are drained first) and return 3 new tokens
+    twin = ids4[[1, 1]].contiguous()
+    ref_twin = O.OracleModel(cfg, sd, "sdpa_math").generate(twin, 5)
+    eos2 = int(ref_twin[0, 9 + 2])
+    stop = dm2.generate(twin if rank == 0 else None, max_new_tokens=40, eos_token_id=eos2, pad_token_id=0)
+    res["eos_stop_ok"] = bool(torch.equal(stop, apply_eos(ref_twin, 9, eos2, 0)) and stop.shape[1] < 9 + 40)
+    res["eos_stop_steps"] = int(getattr(dm2.stage, "n_decode_calls", -1))
+    # left-padded batch with its attention_mask: every row equals its own unpadded generation, pads stay in front
+    lens, Sp, PAD = [9, 6, 9, 4], 9, 3
+    rows = [synthetic_tokens(cfg, 1, L, seed=300 + i)[0] for i, L in enumerate(lens)]
+    pids = torch.full((4, Sp), PAD, dtype=torch.int64)
+    pmask = torch.zeros(4, Sp, dtype=torch.int64)
+    for r, (t, L) in enumerate(zip(rows, lens)):
+        pids[r, Sp - L:], pmask[r, Sp - L:] = t, 1
+    padded = dm2.generate(pids if rank == 0 else None, attention_mask=pmask if rank == 0 else None, max_new_tokens=4,
+                          pad_token_id=PAD)
+    ok = tuple(padded.shape) == (4, Sp + 4) and bool(torch.equal(padded[:, :Sp], pids))
+    for r, (t, L) in enumerate(zip(rows, lens)):
+        want, margins = O.OracleModel(cfg, sd, "sdpa_math").generate(t[None], 4, return_margins=True)
+        for k in range(4):                                  # exact until the first step the oracle itself cannot resolve
+            if margins[0, k] < 0.05:
+                break
+            ok = ok and int(padded[r, Sp + k]) == int(want[0, L + k])
+    res["left_pad_ok"] = ok
     res["gen_equal"] = bool(torch.equal(gen, ref_gen))          # every rank holds the result
     res["gen2_equal"] = bool(torch.equal(gen2, ref_gen2))
     if rank == 0:
