@@ -604,6 +604,8 @@ class StageAdam:
         self.t += 1
         p = self.dm.stage.params
         tr = _trainer(self.dm)
+        if hasattr(tr, "settle_grads"):
+            tr.settle_grads()                  # (a step without a backward since zero_grad(): lazily-zeroed matrices get their zeros)
         if not getattr(tr, "overlap_ok", False) or not p.flat.is_cuda or os.environ.get("TL_ADAM_OVERLAP", "0") != "1":
             self._update(0, p.numel)
             return
