@@ -108,6 +108,12 @@ def main(out_dir):
     if rank == 0:
         s1(tt, labels=tt).loss.backward()
         torch.save(s1.stage.params.g["embed"].cpu(), os.path.join(out_dir, "tied2_ref.pt"))
+    # the same with two micro-batches: deferred weight gradients and the split head backward (the lm_head gradient exists only
+    # after the stage's weight-gradient phase, and is exchanged then)
+    dtie2 = DistributedModel(tc, training=True, n_pipelines=2, max_batch=2, max_seq=32, optimizer=torch.optim.Adam)
+    dtie2(tt if rank == 0 else None, labels=tt if rank == 0 else None).loss.backward()
+    res["tied_split_head"] = bool(dtie2.stage.trainer.head_split) if rank == 1 else None
+    torch.save(dtie2.stage.params.g[key].cpu(), os.path.join(out_dir, f"tied3_{rank}.pt"))
     torch.save(grads, os.path.join(out_dir, f"grads{rank}.pt"))
     torch.save(res, os.path.join(out_dir, f"rank{rank}.pt"))
     dist.barrier()

@@ -44,6 +44,9 @@ def test_two_gpu_pipeline_equals_single_stage(tmp_path):
     a0, a1, ar = torch.load(tmp_path / "tied2_0.pt"), torch.load(tmp_path / "tied2_1.pt"), torch.load(tmp_path / "tied2_ref.pt")
     assert torch.equal(a0, a1)                                        # still equal after an accumulated second backward
     assert (a0.float() - ar.float()).norm() / ar.float().norm() < 5e-3   # = twice the gradient, not 2(E+H)+E+H
+    b0, b1 = torch.load(tmp_path / "tied3_0.pt"), torch.load(tmp_path / "tied3_1.pt")
+    assert r1["tied_split_head"] and torch.equal(b0, b1)              # two micro-batches: split head backward, same exchange
+    assert (b0.float() - tr.float()).norm() / tr.float().norm() < 8e-3
 
 
 @pytest.mark.parametrize("world,rows", [(2, 2), (2, 5), (4, 2)])
