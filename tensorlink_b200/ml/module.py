@@ -105,6 +105,8 @@ EOS_CHECK_EVERY = 16       # decode steps between two host-side "has every row e
 def _eos_list(eos_token_id):
     if eos_token_id is None:
         return []
+    if isinstance(eos_token_id, torch.Tensor):              # HF accepts an int, a list or a tensor of ids
+        return [int(e) for e in eos_token_id.reshape(-1).tolist()]
     return [int(e) for e in eos_token_id] if isinstance(eos_token_id, (list, tuple)) else [int(eos_token_id)]
 
 
