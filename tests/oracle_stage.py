@@ -88,6 +88,16 @@ class OracleStage:
     def params(self):
         return self
 
+    @property
+    def g(self):
+        """gradient views under the arena names the tied-embedding exchange uses (ml/train.py:train_backward)"""
+        out = {}
+        if "model.embed_tokens.weight" in self.sd:
+            out["embed"] = self.sd["model.embed_tokens.weight"].grad
+        if "lm_head.weight" in self.sd:
+            out["head"] = self.sd["lm_head.weight"].grad
+        return out
+
 
 class OracleTrainer:
     """torch-autograd twin of ``StageTrainer`` (same method contract)."""

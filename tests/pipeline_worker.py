@@ -55,8 +55,8 @@ def main(out_dir):
     eos = int(ref_gen2[1, 9 + 2])
     gen_eos = dm2.generate(ids4 if rank == 0 else None, max_new_tokens=5, eos_token_id=eos, pad_token_id=0)
     res["eos_ok"] = bool(torch.equal(gen_eos, apply_eos(ref_gen2, 9, eos, 0)) and gen_eos.shape[1] <= ref_gen2.shape[1])
-    # ... and the loop really stops: 40 tokens requested, both rows (copies of one prompt) emit EOS at step 2, the ranks agree
-    # at the step-16 check (ids in flight are drained first) and return 3 new tokens
+    # ... and the loop really stops: 40 tokens requested, both rows (copies of one prompt) emit EOS within the first 3 steps, the ranks agree
+    # at the step-16 check (ids in flight are drained first) and return the prompt plus the tokens up to that EOS
     twin = ids4[[1, 1]].contiguous()
     ref_twin = O.OracleModel(cfg, sd, "sdpa_math").generate(twin, 5)
     eos2 = int(ref_twin[0, 9 + 2])
@@ -80,6 +80,18 @@ def main(out_dir):
                 break
             ok = ok and int(padded[r, Sp + k]) == int(want[0, L + k])
     res["left_pad_ok"] = ok
+    # a batch the requested micro-batch count does not divide (3 rows, n_pipelines = 2 -> one micro-batch of 3 rows)
+    ids3 = synthetic_tokens(cfg, 3, 7, seed=77)
+    dm3 = DistributedModel(cfg, training=False, n_pipelines=2, max_batch=6, max_seq=64, _stage_factory=OracleStage)
+    gen3 = dm3.generate(ids3 if rank == 0 else None, max_new_tokens=4)
+    res["odd_batch_ok"] = bool(torch.equal(gen3, O.OracleModel(cfg, sd, "sdpa_math").generate(ids3, 4)))
+    # streamer + early stop: the callback sees exactly the columns the (stopped) loop produced, then end()
+    st2 = Streamer()
+    stop2 = dm2.generate(twin if rank == 0 else None, max_new_tokens=40, eos_token_id=eos2, pad_token_id=0, streamer=st2)
+    if rank == 0:
+        cols = torch.stack(st2.cols, 1)
+        k = stop2.shape[1] - 9                 # new tokens that survive the EOS trim; the streamer saw at least those
+        res["stream_stop_ok"] = bool(st2.ended and 1 <= k <= cols.shape[1] < 40 and torch.equal(cols[:, :k], stop2[:, 9:]))
     res["gen_equal"] = bool(torch.equal(gen, ref_gen))          # every rank holds the result
     res["gen2_equal"] = bool(torch.equal(gen2, ref_gen2))
     if rank == 0:
@@ -101,6 +113,19 @@ def main(out_dir):
     res["grad_worst_rel_l2"] = worst
     res["n_params_with_grad"] = sum(v.grad is not None for v in dmt.stage.sd.values())
     res["bytes_sent"] = dmt.link.bytes_sent
+    # tied embeddings split over the two ranks (embedding on rank 0, lm_head on rank 1): after backward both copies hold
+    # embedding gradient + lm_head gradient = the single-process gradient of the shared tensor
+    tcfg = C.TINY_QWEN2
+    tsd = init_state_dict(tcfg)
+    dtie = DistributedModel(tcfg, training=True, n_pipelines=2, max_batch=4, max_seq=64, _stage_factory=OracleStage,
+                            optimizer=torch.optim.Adam)
+    tt = synthetic_tokens(tcfg, 4, 12)
+    dtie(tt if rank == 0 else None, labels=tt if rank == 0 else None).loss.backward()
+    rsd = {k: v.clone().requires_grad_(True) for k, v in tsd.items()}
+    rsd["lm_head.weight"] = rsd["model.embed_tokens.weight"]
+    O.OracleModel(tcfg, rsd, "sdpa_math").loss(tt, tt)[0].backward()
+    mine = dtie.stage.sd["model.embed_tokens.weight" if rank == 0 else "lm_head.weight"].grad
+    res["tied_rel_l2"] = O.rel_l2(mine, rsd["model.embed_tokens.weight"].grad)
     torch.save(res, os.path.join(out_dir, f"rank{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()

@@ -28,6 +28,8 @@ def test_two_rank_pipeline(tmp_path):
     assert r0["gen_equal"] and r1["gen_equal"] and r0["gen2_equal"] and r1["gen2_equal"]
     assert r0["stream_ok"] and r0["eos_ok"] and r1["eos_ok"]
     assert r0["eos_stop_ok"] and r1["eos_stop_ok"] and r0["left_pad_ok"] and r1["left_pad_ok"]
+    assert r0["odd_batch_ok"] and r1["odd_batch_ok"] and r0["stream_stop_ok"]
+    assert r0["tied_rel_l2"] < 2e-2 and r1["tied_rel_l2"] < 2e-2
     assert r0["loss_close"] and r1["loss_close"]
     # bf16 autograd in two halves (grad crossing the rank boundary rounded to bf16 once more) vs one graph
     assert r0["grad_worst_rel_l2"] < 2e-2 and r1["grad_worst_rel_l2"] < 2e-2
