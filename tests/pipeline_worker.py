@@ -124,8 +124,11 @@ def main(out_dir):
     rsd = {k: v.clone().requires_grad_(True) for k, v in tsd.items()}
     rsd["lm_head.weight"] = rsd["model.embed_tokens.weight"]
     O.OracleModel(tcfg, rsd, "sdpa_math").loss(tt, tt)[0].backward()
-    mine = dtie.stage.sd["model.embed_tokens.weight" if rank == 0 else "lm_head.weight"].grad
-    res["tied_rel_l2"] = O.rel_l2(mine, rsd["model.embed_tokens.weight"].grad)
+    if dtie.link.first or dtie.link.last:
+        mine = dtie.stage.sd["model.embed_tokens.weight" if dtie.link.first else "lm_head.weight"].grad
+        res["tied_rel_l2"] = O.rel_l2(mine, rsd["model.embed_tokens.weight"].grad)
+    else:
+        res["tied_rel_l2"] = 0.0                # a middle stage holds neither copy
     torch.save(res, os.path.join(out_dir, f"rank{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()

@@ -1,10 +1,12 @@
-"""world_size-2 CPU (gloo) test of the pipeline host logic: plan -> stages, forward hops, generate with ids hopping
-back, micro-batch rotation, streaming, loss broadcast, backward routing."""
+"""CPU (gloo) tests of the pipeline host logic with world_size 2 and 3 (first / middle / last stage): plan -> stages, forward
+hops, generate with ids hopping back, micro-batch rotation, streaming, EOS early stop, left-padded batches, loss
+broadcast, backward routing, tied embeddings on two ranks."""
 import os
 import socket
 import subprocess
 import sys
 
+import pytest
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -16,22 +18,20 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def test_two_rank_pipeline(tmp_path):
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+@pytest.mark.parametrize("world", [2, 3])
+def test_pipeline_host_logic(tmp_path, world):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "pipeline_worker.py"), str(tmp_path)]
     env = dict(os.environ, OMP_NUM_THREADS="2", PYTHONPATH=ROOT)
-    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
     errs = "".join(open(p).read() for p in sorted(map(str, tmp_path.glob("err*.txt"))))
     assert r.returncode == 0, errs or r.stderr[-3000:]
-    r0, r1 = torch.load(tmp_path / "rank0.pt"), torch.load(tmp_path / "rank1.pt")
-    assert r0["logits_equal"]
-    assert r0["gen_equal"] and r1["gen_equal"] and r0["gen2_equal"] and r1["gen2_equal"]
-    assert r0["stream_ok"] and r0["eos_ok"] and r1["eos_ok"]
-    assert r0["eos_stop_ok"] and r1["eos_stop_ok"] and r0["left_pad_ok"] and r1["left_pad_ok"]
-    assert r0["odd_batch_ok"] and r1["odd_batch_ok"] and r0["stream_stop_ok"]
-    assert r0["tied_rel_l2"] < 2e-2 and r1["tied_rel_l2"] < 2e-2
-    assert r0["loss_close"] and r1["loss_close"]
-    # bf16 autograd in two halves (grad crossing the rank boundary rounded to bf16 once more) vs one graph
-    assert r0["grad_worst_rel_l2"] < 2e-2 and r1["grad_worst_rel_l2"] < 2e-2
-    assert r0["n_params_with_grad"] > 10 and r1["n_params_with_grad"] > 10
-    assert r0["bytes_sent"] > 0 and r1["bytes_sent"] > 0
+    res = [torch.load(tmp_path / f"rank{i}.pt") for i in range(world)]
+    r0 = res[0]
+    assert r0["logits_equal"] and r0["stream_ok"] and r0["stream_stop_ok"]
+    for r_ in res:                                                  # every rank holds every result
+        assert r_["gen_equal"] and r_["gen2_equal"] and r_["eos_ok"] and r_["eos_stop_ok"] and r_["left_pad_ok"] and r_["odd_batch_ok"]
+        assert r_["loss_close"]
+        # bf16 autograd in pieces (a gradient crossing a rank boundary is rounded to bf16 once more) vs one graph
+        assert r_["grad_worst_rel_l2"] < 2e-2 and r_["tied_rel_l2"] < 2e-2
+        assert r_["n_params_with_grad"] >= 9 and r_["bytes_sent"] > 0
