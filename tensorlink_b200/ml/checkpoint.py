@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import json
 import os
-from typing import Dict, Iterator, Optional
+from typing import Dict, Iterator
 
 import torch
 

@@ -10,7 +10,7 @@ produced by the reference's planner is accepted by ``DistributedModel(config=...
 """
 from __future__ import annotations
 
-from typing import Dict, List, Sequence
+from typing import Dict, List
 
 from .configs import ShardModelConfig
 

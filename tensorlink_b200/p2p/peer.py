@@ -16,7 +16,7 @@ decode graph begins with ``tl_peer_wait`` (csrc/peer.cu).  Send/wait counters ar
 """
 from __future__ import annotations
 
-from typing import List, Optional
+from typing import List
 
 import torch
 

@@ -22,7 +22,7 @@ reference's own processes.  tests/test_wire_cpu.py pins `encode` byte-for-byte t
 from __future__ import annotations
 
 import json
-from typing import Any, Dict, List, Tuple
+from typing import Any, Dict, Tuple
 
 import torch
 from safetensors.torch import load as _blob_load
