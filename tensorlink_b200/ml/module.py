@@ -237,8 +237,22 @@ class DistributedModel(torch.nn.Module):
         """module.py:577-650: this rank's parameters under their HF names (values, not nn.Parameters)."""
         return iter(self.stage.params.hf_state_dict().values())
 
-    def state_dict(self, *a, **k):
-        return self.stage.params.hf_state_dict()
+    def state_dict(self, *a, gather: bool = False, **k):
+        """This rank's tensors under their HF names.  ``gather=True``: the WHOLE model's state dict on the first rank, on the
+        host (what the reference's ``parameters(distributed=True, load=True)`` pulls from its workers, module.py:577-650);
+        the other ranks get their own part.  For checkpoints prefer ``save_pretrained`` (each stage writes its own file)."""
+        sd = self.stage.params.hf_state_dict()
+        if not gather or self.world == 1:
+            return sd
+        parts = self.link.gather_object({k_: v.detach().cpu() for k_, v in sd.items()}, 0)
+        if not self.link.first:
+            return sd
+        whole: Dict[str, torch.Tensor] = {}
+        for part in parts:
+            whole.update(part)
+        if self.cfg.tied and "lm_head.weight" in whole and "model.embed_tokens.weight" in whole:
+            whole["lm_head.weight"] = whole["model.embed_tokens.weight"]      # one tensor under both names, like HF
+        return whole
 
     def save_pretrained(self, path: str):
         """Write this job's weights as an HF-layout checkpoint (one safetensors file per stage + index + config)."""

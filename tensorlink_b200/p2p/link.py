@@ -144,6 +144,24 @@ class StageLink:
         dist.broadcast_object_list(box, src=src, group=self.down)
         return box[0]
 
+    def gather_object(self, obj, dst: int = 0):
+        """every rank's ``obj`` as a list on ``dst`` (None elsewhere)"""
+        if self.world == 1:
+            return [obj]
+        # point-to-point object transfers in rank order (works on every backend; nothing lands on ranks that do not need it)
+        if self.rank != dst:
+            dist.send_object_list([obj], dst=dst, group=self.down)
+            return None
+        out = []
+        for src in range(self.world):
+            if src == dst:
+                out.append(obj)
+            else:
+                box = [None]
+                dist.recv_object_list(box, src=src, group=self.down)
+                out.append(box[0])
+        return out
+
     def all_gather_object(self, obj) -> list:
         if self.world == 1:
             return [obj]

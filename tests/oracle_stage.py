@@ -88,6 +88,9 @@ class OracleStage:
     def params(self):
         return self
 
+    def hf_state_dict(self, grads: bool = False):
+        return {k: (v.grad if grads else v.detach()) for k, v in self.sd.items() if not (grads and v.grad is None)}
+
     @property
     def g(self):
         """gradient views under the arena names the tied-embedding exchange uses (ml/train.py:train_backward)"""

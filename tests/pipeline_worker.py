@@ -33,6 +33,12 @@ def main(out_dir):
         with torch.no_grad():
             ref = O.OracleModel(cfg, sd, "sdpa_math").logits(ids)
         res["logits_equal"] = bool(torch.equal(out.logits, ref))
+    # the whole model's state dict gathered on the first rank (reference: parameters(distributed=True, load=True))
+    whole = dm.state_dict(gather=True)
+    if rank == 0:
+        res["gather_ok"] = bool(set(whole) == set(sd) and all(torch.equal(whole[k], sd[k]) for k in sd))
+    else:
+        res["gather_ok"] = bool(0 < len(whole) < len(sd))
     # 2) greedy generate, single micro-batch and 2 micro-batches in flight; streaming callback on rank 0
     class Streamer:
         def __init__(self):
